@@ -1,0 +1,146 @@
+/*
+ * sloth_b200.h -- C ABI of the B200 raster path (libsloth_b200.so).
+ *
+ * The reference (ecumene/rust-sloth) has no plugin/FFI interface: its raster
+ * path is the group of Rust calls made once per frame from src/main.rs:76-89
+ *
+ *     let rot = Rotation3::from_euler_angles(..).to_homogeneous();   main.rs:76-77
+ *     context.update(size, &mesh_queue)?;                            main.rs:78   (context.rs:93-141)
+ *     context.clear();                                               main.rs:79   (context.rs:35-45)
+ *     for mesh in &mesh_queue { draw_mesh(&mut context, &mesh, rot, default_shader); }   main.rs:80-83
+ *     context.flush(..)   <- reads context.frame_buffer                main.rs:89   (context.rs:50-92)
+ *
+ * A Rust host replaces exactly that group with the calls below (extern "C"
+ * block + build.rs shown in INTEGRATION.md).  Conventions: every function
+ * returns 0 on success and a negative SLOTH_E_* code on failure, with a
+ * human-readable message available from sloth_last_error() (thread-local);
+ * nothing is thrown across the boundary; the caller owns every host buffer;
+ * device memory belongs to the context; a context is bound to one GPU and is
+ * not thread-safe (use one context per host thread / per GPU).
+ *
+ * There is NO CPU fallback: if no CUDA device is usable, sloth_ctx_create
+ * fails with SLOTH_E_CUDA.
+ *
+ * Frame-buffer cell format (replaces `(char, (u8,u8,u8))`, context.rs:16):
+ *     uint32 cell = glyph | r << 8 | g << 16 | b << 24        (glyph is ASCII)
+ * blank = (' ',0,0,0), image-mode row marker = ('\n',0,0,0)  (rasterizer.rs:89-91).
+ * Matrices are column-major float[16], like nalgebra's Matrix4<f32> storage.
+ */
+#ifndef SLOTH_B200_H
+#define SLOTH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLOTH_API __attribute__((visibility("default")))
+
+enum {
+    SLOTH_OK = 0,
+    SLOTH_E_ARG = -1,      /* bad argument (null pointer, zero size, out of range) */
+    SLOTH_E_CUDA = -2,     /* CUDA runtime error / no usable device */
+    SLOTH_E_STATE = -3,    /* call order (render before scene_set / resize) */
+    SLOTH_E_TOO_LARGE = -4 /* more than 2^27-1 triangles, or W*H+H >= 2^31, or W/H > 65535 */
+};
+
+typedef struct sloth_ctx sloth_ctx;
+
+/* Context::blank(image)  -- src/context.rs:22-34.  `device` = CUDA ordinal. */
+SLOTH_API int sloth_ctx_create(int device, int image_mode, sloth_ctx **out);
+SLOTH_API int sloth_ctx_destroy(sloth_ctx *ctx);
+
+/*
+ * The mesh queue (main.rs:31, inputs.rs:95-129) as one triangle soup in draw
+ * order (mesh order, then triangle order: main.rs:80-83, rasterizer.rs:43-45).
+ *   xyz  n_tri*9 floats: v1.xyz v2.xyz v3.xyz, w = 1 implied (geometry.rs:17-23)
+ *   rgb  n_tri*3 bytes:  Triangle.color
+ *   scene_max  fold(max) over meshes of bounding_box.max.{x,y,z} starting at
+ *              0.0 -- the `scale` loop of Context::update, context.rs:106-113.
+ * Uploaded once; the soup stays resident in HBM (40 B/triangle).
+ */
+SLOTH_API int sloth_scene_set(sloth_ctx *ctx, const float *xyz, const uint8_t *rgb, size_t n_tri,
+                              float scene_max);
+
+/* match_dimensions (inputs.rs:159-169) / the size adoption in Context::update
+ * (context.rs:134-137).  (Re)allocates the frame state for W x H cells. */
+SLOTH_API int sloth_ctx_resize(sloth_ctx *ctx, uint32_t width, uint32_t height);
+
+/*
+ * One frame = update + clear + draw_mesh over the whole queue (main.rs:78-83).
+ *   rot        the `transform` passed to draw_mesh (column-major 4x4)
+ *   cells_out  host buffer, W*H cells (+H in image mode, context.rs:36-41)
+ *   z_out      optional host buffer, W*H floats = Context.z_buffer after the
+ *              frame (may be NULL).  A winning -0.0 is reported as +0.0.
+ */
+SLOTH_API int sloth_render(sloth_ctx *ctx, const float rot[16], uint32_t *cells_out, float *z_out);
+
+/* The -j / turntable loop (main.rs:60-111): n_frames frames, frame k uses
+ * rots[16*k ..], written to cells_out + k*cells_per_frame.  Device work and
+ * device->host copies are pipelined across frames. */
+SLOTH_API int sloth_render_batch(sloth_ctx *ctx, const float *rots, size_t n_frames, uint32_t *cells_out);
+
+/* Same frame, but the result stays on the device: d_cells is a device pointer
+ * (same GPU) to W*H(+H) cells -- or band_rows*W cells when a band is set.
+ * Runs on the context's stream; sloth_ctx_sync() waits for it. */
+SLOTH_API int sloth_render_device(sloth_ctx *ctx, const float rot[16], void *d_cells);
+SLOTH_API int sloth_ctx_sync(sloth_ctx *ctx);
+
+/*
+ * Row-band mode for one huge frame split across GPUs: this context produces
+ * only cells of rows [row0, row1) (destination rows: a fragment that wraps
+ * past the end of row y belongs to row y+1, rasterizer.rs:80).  The output
+ * of sloth_render_device is then (row1-row0)*W cells; the image-mode tail
+ * (H blank cells) is produced by whoever assembles the frame.
+ * row0 = row1 = 0 restores whole-frame mode.
+ */
+SLOTH_API int sloth_ctx_set_band(sloth_ctx *ctx, uint32_t row0, uint32_t row1);
+
+/* The `shader: F` closure of draw_mesh (rasterizer.rs:39-41), restricted to
+ * what the reference ever passes: 9 ascending `<=` thresholds and 10 glyphs
+ * (the last one for "above all thresholds or NaN").  Default = default_shader,
+ * rasterizer.rs:5-27. */
+SLOTH_API int sloth_shader_set(sloth_ctx *ctx, const float thr[9], const char glyph[10]);
+
+typedef struct sloth_stats {
+    uint64_t frames;           /* frames rendered by this context */
+    uint64_t kernel_launches;  /* CUDA kernels launched by this library */
+    uint64_t fragments;        /* covered fragments (depth tests) of the last frame; needs count_fragments */
+    uint32_t n_tri;
+    uint32_t walk_tris;        /* last frame: triangles sent to the warp-per-row-band kernel */
+    uint32_t walk_items;       /* last frame: row-band work items */
+    uint32_t irregular_tris;   /* last frame: triangles sent to the brute-force kernel */
+    uint32_t stamp_fixups;     /* last frame: newline-vs-wrapped-fragment order fix-ups */
+    float last_frame_ms;       /* device time of the last sloth_render / per frame of the last batch */
+    float geom_ms, walk_ms, resolve_ms; /* per-kernel device times of the last sloth_render when timing is on */
+} sloth_stats;
+
+SLOTH_API int sloth_stats_get(sloth_ctx *ctx, sloth_stats *out);
+/* flags: bit 0 = count fragments (adds atomics; off by default), bit 1 = per-kernel event timing */
+SLOTH_API int sloth_stats_enable(sloth_ctx *ctx, uint32_t flags);
+
+SLOTH_API const char *sloth_last_error(void);
+
+/* ---- host-side helpers (no GPU work): the scalar arithmetic around the path ---- */
+
+/* Rotation3::from_euler_angles(roll,pitch,yaw).to_homogeneous(), main.rs:76-77
+ * (libm sinf/cosf on the host, like Rust's f32::sin_cos). */
+SLOTH_API void sloth_rotation_from_euler(float roll, float pitch, float yaw, float out[16]);
+/* Context::update's matrix, context.rs:93-133 (sizes taken `as u16`). */
+SLOTH_API void sloth_utransform(uint32_t width, uint32_t height, float scene_max, float out[16]);
+/* pitch sequence of `image -j N` starting from the -y argument (inputs.rs:131-149,
+ * main.rs:55-58,92-106); returns the number of frames the reference renders. */
+SLOTH_API size_t sloth_turntable_pitches(float y_arg, uint32_t n_frames, float *out, size_t cap);
+/* Page-locked host memory for cells_out: device->host copies of a batch only
+ * overlap with rendering when the destination is pinned. */
+SLOTH_API int sloth_pinned_alloc(size_t bytes, void **out);
+SLOTH_API int sloth_pinned_free(void *ptr);
+/* number of cells per frame for this context: W*H (+H in image mode), or band size */
+SLOTH_API size_t sloth_cells_per_frame(const sloth_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLOTH_B200_H */

@@ -1,0 +1,454 @@
+"""rust_sloth_b200 -- B200-native raster path of ecumene/rust-sloth.
+
+Host-side mirror (Python over ctypes) of the reference's public items on the
+raster path, bound to the C ABI in ``include/sloth_b200.h``:
+
+==========================  ===========================================
+reference (Rust)            here
+==========================  ===========================================
+``Context::blank``          :meth:`Context.blank`            context.rs:22
+``match_dimensions``        ``ctx.width / ctx.height``       inputs.rs:159
+``Context::update``         :meth:`Context.update`           context.rs:93
+``Context::clear``          :meth:`Context.clear`            context.rs:35
+``draw_mesh``               :func:`draw_mesh`                rasterizer.rs:39
+``Context.frame_buffer``    :attr:`Context.frame_buffer`     context.rs:16
+``Context.z_buffer``        :attr:`Context.z_buffer`         context.rs:17
+``Context::flush``          :meth:`Context.flush`            context.rs:50
+``default_shader``          :func:`default_shader`           rasterizer.rs:5
+``match_meshes``            :func:`match_meshes`             inputs.rs:95
+``match_turntable`` + loop  :func:`turntable_pitches`        inputs.rs:131, main.rs:55-106
+==========================  ===========================================
+
+The directory is called ``rust-sloth_b200`` (not importable as written); the
+root-level ``rust_sloth_b200.py`` shim loads it under this legal name.
+
+There is no CPU fallback: importing works anywhere, but creating a
+:class:`Context` raises :class:`SlothError` when ``libsloth_b200.so`` is
+missing or no CUDA device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsloth_b200.so")
+HOST_LIB_PATH = os.path.join(_HERE, "libsloth_host.so")
+
+SLOTH_OK, SLOTH_E_ARG, SLOTH_E_CUDA, SLOTH_E_STATE, SLOTH_E_TOO_LARGE = 0, -1, -2, -3, -4
+
+# every symbol include/sloth_b200.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "sloth_ctx_create", "sloth_ctx_destroy", "sloth_scene_set", "sloth_ctx_resize", "sloth_render",
+    "sloth_render_batch", "sloth_render_device", "sloth_ctx_sync", "sloth_ctx_set_band",
+    "sloth_shader_set", "sloth_stats_get", "sloth_stats_enable", "sloth_last_error",
+    "sloth_rotation_from_euler", "sloth_utransform", "sloth_turntable_pitches", "sloth_cells_per_frame",
+    "sloth_pinned_alloc", "sloth_pinned_free",
+]
+
+
+class SlothError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"sloth_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("frames", C.c_uint64), ("kernel_launches", C.c_uint64), ("fragments", C.c_uint64),
+        ("n_tri", C.c_uint32), ("walk_tris", C.c_uint32), ("walk_items", C.c_uint32),
+        ("irregular_tris", C.c_uint32), ("stamp_fixups", C.c_uint32),
+        ("last_frame_ms", C.c_float), ("geom_ms", C.c_float), ("walk_ms", C.c_float),
+        ("resolve_ms", C.c_float),
+    ]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+_host = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SlothError(SLOTH_E_CUDA, f"{LIB_PATH} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    fp, vp = C.POINTER(C.c_float), C.c_void_p
+    L.sloth_ctx_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    L.sloth_ctx_destroy.argtypes = [vp]
+    L.sloth_scene_set.argtypes = [vp, fp, C.POINTER(C.c_uint8), C.c_size_t, C.c_float]
+    L.sloth_ctx_resize.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.sloth_render.argtypes = [vp, fp, C.POINTER(C.c_uint32), fp]
+    L.sloth_render_batch.argtypes = [vp, fp, C.c_size_t, C.POINTER(C.c_uint32)]
+    L.sloth_render_device.argtypes = [vp, fp, vp]
+    L.sloth_ctx_sync.argtypes = [vp]
+    L.sloth_ctx_set_band.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.sloth_shader_set.argtypes = [vp, fp, C.c_char_p]
+    L.sloth_stats_get.argtypes = [vp, C.POINTER(Stats)]
+    L.sloth_stats_enable.argtypes = [vp, C.c_uint32]
+    L.sloth_last_error.restype = C.c_char_p
+    L.sloth_rotation_from_euler.argtypes = [C.c_float, C.c_float, C.c_float, fp]
+    L.sloth_rotation_from_euler.restype = None
+    L.sloth_utransform.argtypes = [C.c_uint32, C.c_uint32, C.c_float, fp]
+    L.sloth_utransform.restype = None
+    L.sloth_turntable_pitches.argtypes = [C.c_float, C.c_uint32, fp, C.c_size_t]
+    L.sloth_turntable_pitches.restype = C.c_size_t
+    L.sloth_cells_per_frame.argtypes = [vp]
+    L.sloth_cells_per_frame.restype = C.c_size_t
+    L.sloth_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.sloth_pinned_free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != SLOTH_OK:
+        raise SlothError(rc, load_library().sloth_last_error().decode("utf-8", "replace"))
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+# --------------------------------------------------------------------------------------
+# geometry.rs mirrors
+# --------------------------------------------------------------------------------------
+@dataclass
+class AABB:  # geometry.rs:5-15
+    min: np.ndarray
+    max: np.ndarray
+
+
+class SimpleMesh:
+    """geometry.rs:78-81 as a soup: ``xyz`` (n,9) f32, ``rgb`` (n,3) u8, ``bounding_box``."""
+
+    def __init__(self, xyz, rgb, bbox_min=None, bbox_max=None):
+        self.xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 9)
+        self.rgb = np.ascontiguousarray(rgb, np.uint8).reshape(-1, 3)
+        if self.xyz.shape[0] != self.rgb.shape[0]:
+            raise ValueError("xyz and rgb disagree on the triangle count")
+        if bbox_max is None:  # OBJ rule: the fold starts at 0 (geometry.rs:85-88)
+            pts = self.xyz.reshape(-1, 3)
+            zero = np.zeros(3, np.float32)
+            bbox_min = np.minimum(pts.min(axis=0), zero) if len(pts) else zero
+            bbox_max = np.maximum(pts.max(axis=0), zero) if len(pts) else zero
+        self.bounding_box = AABB(np.asarray(bbox_min, np.float32), np.asarray(bbox_max, np.float32))
+
+    def __len__(self) -> int:
+        return self.xyz.shape[0]
+
+
+def scene_scale0(meshes) -> np.float32:
+    """context.rs:106-113: fold(max) of bounding_box.max.{x,y,z} over meshes, from 0.0."""
+    s = np.float32(0.0)
+    for m in meshes:
+        for d in range(3):
+            s = np.fmax(s, np.float32(m.bounding_box.max[d]))
+    return np.float32(s)
+
+
+class _HostScene(C.Structure):
+    _fields_ = [("xyz", C.POINTER(C.c_float)), ("rgb", C.POINTER(C.c_uint8)), ("n_tri", C.c_size_t),
+                ("n_meshes", C.c_size_t), ("mesh_sizes", C.POINTER(C.c_size_t)),
+                ("mesh_bbox", C.POINTER(C.c_float)), ("scale0", C.c_float), ("error", C.c_char * 512)]
+
+
+def _host_lib() -> C.CDLL:
+    global _host
+    if _host is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise SlothError(SLOTH_E_STATE, f"{HOST_LIB_PATH} is missing -- run __graft_entry__.build()")
+        H = C.CDLL(HOST_LIB_PATH)
+        H.sloth_host_load.argtypes = [C.c_char_p]
+        H.sloth_host_load.restype = C.POINTER(_HostScene)
+        H.sloth_host_free.argtypes = [C.POINTER(_HostScene)]
+        _host = H
+    return _host
+
+
+def match_meshes(arg: str) -> list[SimpleMesh]:
+    """inputs.rs:95-129: one CLI value, split on ' ', OBJ via tobj rules, STL via stl_io rules."""
+    H = _host_lib()
+    sp = H.sloth_host_load(arg.encode())
+    try:
+        s = sp.contents
+        if s.error:
+            raise SlothError(SLOTH_E_ARG, s.error.decode("utf-8", "replace"))
+        n = s.n_tri
+        xyz = np.ctypeslib.as_array(s.xyz, shape=(n * 9,)).copy().reshape(n, 9) if n else np.zeros((0, 9), np.float32)
+        rgb = np.ctypeslib.as_array(s.rgb, shape=(n * 3,)).copy().reshape(n, 3) if n else np.zeros((0, 3), np.uint8)
+        meshes, off = [], 0
+        for i in range(s.n_meshes):
+            k = s.mesh_sizes[i]
+            bb = [s.mesh_bbox[i * 6 + d] for d in range(6)]
+            meshes.append(SimpleMesh(xyz[off:off + k], rgb[off:off + k], bb[:3], bb[3:]))
+            off += k
+        return meshes
+    finally:
+        H.sloth_host_free(sp)
+
+
+# --------------------------------------------------------------------------------------
+# rasterizer.rs / main.rs mirrors
+# --------------------------------------------------------------------------------------
+DEFAULT_THRESHOLDS = np.array([0.20, 0.30, 0.40, 0.50, 0.60, 0.70, 0.80, 0.90, 1.0], np.float32)
+DEFAULT_GLYPHS = b".:-=+*#%@ "
+
+
+def default_shader(shade) -> str:
+    """rasterizer.rs:5-27 (host copy; the device evaluates the same table per fragment)."""
+    shade = np.float32(shade)
+    for t, g in zip(DEFAULT_THRESHOLDS, DEFAULT_GLYPHS[:9]):
+        if shade <= t:
+            return chr(g)
+    return " "
+
+
+def rotation_from_euler(roll: float, pitch: float, yaw: float) -> np.ndarray:
+    """Rotation3::from_euler_angles(..).to_homogeneous(), main.rs:76-77; column-major float32[16]."""
+    out = np.empty(16, np.float32)
+    load_library().sloth_rotation_from_euler(np.float32(roll), np.float32(pitch), np.float32(yaw), _fp(out))
+    return out
+
+
+def utransform(width: int, height: int, scene_max: float) -> np.ndarray:
+    out = np.empty(16, np.float32)
+    load_library().sloth_utransform(width, height, np.float32(scene_max), _fp(out))
+    return out
+
+
+def turntable_pitches(y_arg: float, n_frames: int) -> np.ndarray:
+    """Pitch of every frame `image -j N` renders (inputs.rs:131-149, main.rs:55-58,92-106)."""
+    L = load_library()
+    cap = max(int(n_frames), 1) + 4
+    buf = np.empty(cap, np.float32)
+    n = L.sloth_turntable_pitches(np.float32(y_arg), int(n_frames), _fp(buf), cap)
+    return buf[:n].copy()
+
+
+class PinnedBuffer:
+    """Page-locked host memory for the frame buffers of a batch (cudaHostAlloc)."""
+
+    def __init__(self, n_cells: int):
+        self._ptr = C.c_void_p()
+        self.n = int(n_cells)
+        _check(load_library().sloth_pinned_alloc(max(self.n, 1) * 4, C.byref(self._ptr)))
+        self.array = np.ctypeslib.as_array(C.cast(self._ptr, C.POINTER(C.c_uint32)), shape=(max(self.n, 1),))[:self.n]
+
+    def free(self):
+        if self._ptr:
+            load_library().sloth_pinned_free(self._ptr)
+            self._ptr = C.c_void_p()
+            self.array = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """context.rs:12-19.  Owns one GPU context; not thread-safe (one per thread / GPU)."""
+
+    def __init__(self, image: bool, device: int = 0):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        _check(self._L.sloth_ctx_create(device, 1 if image else 0, C.byref(self._h)))
+        self.image = bool(image)
+        self.device = device
+        self.width = 0
+        self.height = 0
+        self.utransform = np.eye(4, dtype=np.float32).T.reshape(16).copy()
+        self._sized = (0, 0)
+        self._scene_id = None
+        self._scene_max = np.float32(0)
+        self._band = (0, 0)
+        self._pending_rot = None
+        self._frame = None
+        self._z = None
+
+    @classmethod
+    def blank(cls, image: bool, device: int = 0) -> "Context":
+        return cls(image, device)
+
+    def close(self):
+        if self._h:
+            self._L.sloth_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- scene / size ------------------------------------------------------------------
+    def set_scene(self, xyz: np.ndarray, rgb: np.ndarray, scene_max: float) -> None:
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 9)
+        rgb = np.ascontiguousarray(rgb, np.uint8).reshape(-1, 3)
+        _check(self._L.sloth_scene_set(self._h, _fp(xyz), rgb.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                       xyz.shape[0], np.float32(scene_max)))
+        self._scene_max = np.float32(scene_max)
+        self.n_tri = xyz.shape[0]
+
+    def resize(self, width: int, height: int) -> None:
+        _check(self._L.sloth_ctx_resize(self._h, int(width), int(height)))
+        self.width, self.height = int(width), int(height)
+        self._sized = (self.width, self.height)
+        self._band = (0, 0)
+
+    def set_band(self, row0: int, row1: int) -> None:
+        _check(self._L.sloth_ctx_set_band(self._h, int(row0), int(row1)))
+        self._band = (int(row0), int(row1))
+
+    def update(self, old_size, meshes) -> None:
+        """Context::update (context.rs:93-141): adopts the size and the scene scale.
+
+        The mesh queue is uploaded the first time (or when a different list is passed)."""
+        del old_size  # the reference passes a by-value (0,0) every frame (main.rs:53,78)
+        if (self.width, self.height) != self._sized:
+            self.resize(self.width, self.height)
+        key = tuple(id(m) for m in meshes)
+        if key != self._scene_id:
+            xyz = np.concatenate([m.xyz for m in meshes]) if meshes else np.zeros((0, 9), np.float32)
+            rgb = np.concatenate([m.rgb for m in meshes]) if meshes else np.zeros((0, 3), np.uint8)
+            self.set_scene(xyz, rgb, scene_scale0(meshes))
+            self._scene_id = key
+            self._meshes = list(meshes)
+        self.utransform = utransform(self.width, self.height, self._scene_max)
+
+    def clear(self) -> None:
+        """Context::clear (context.rs:35-45): starts a new frame."""
+        self._pending_rot = None
+        self._drawn = []
+        self._frame = None
+        self._z = None
+
+    def _draw(self, mesh, transform) -> None:
+        rot = np.ascontiguousarray(transform, np.float32).reshape(16)
+        if self._pending_rot is not None and not np.array_equal(self._pending_rot.view(np.uint32), rot.view(np.uint32)):
+            raise NotImplementedError("all draw_mesh calls of one frame must use the same transform "
+                                      "(the reference's only caller does, main.rs:80-83)")
+        self._pending_rot = rot
+        self._drawn.append(mesh)
+        self._frame = None
+
+    def _resolve(self, want_z: bool = False) -> None:
+        if self._frame is not None and (self._z is not None or not want_z):
+            return
+        drawn = getattr(self, "_drawn", [])
+        if [id(m) for m in drawn] != [id(m) for m in getattr(self, "_meshes", [])]:
+            raise NotImplementedError("a frame must draw exactly the mesh queue passed to update(), in order")
+        if self._pending_rot is None:
+            raise SlothError(SLOTH_E_STATE, "nothing drawn since clear()")
+        self._frame, self._z = self.render(self._pending_rot, want_z=want_z)
+
+    @property
+    def frame_buffer(self) -> np.ndarray:
+        """uint32 cells: glyph | r<<8 | g<<16 | b<<24 (the reference's Vec<(char,(u8,u8,u8))>)."""
+        self._resolve()
+        return self._frame
+
+    @property
+    def z_buffer(self) -> np.ndarray:
+        self._resolve(want_z=True)
+        return self._z
+
+    # -- direct entry points -----------------------------------------------------------
+    def cells_per_frame(self) -> int:
+        return int(self._L.sloth_cells_per_frame(self._h))
+
+    def render(self, rot: np.ndarray, want_z: bool = False):
+        rot = np.ascontiguousarray(rot, np.float32).reshape(16)
+        cells = np.empty(self.cells_per_frame(), np.uint32)
+        z = np.empty(self.width * self.height, np.float32) if want_z else None
+        _check(self._L.sloth_render(self._h, _fp(rot), cells.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                    _fp(z) if want_z else None))
+        return cells, z
+
+    def render_batch(self, rots: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        rots = np.ascontiguousarray(rots, np.float32).reshape(-1, 16)
+        n = rots.shape[0]
+        cpf = self.cells_per_frame()
+        if out is None:
+            out = np.empty(n * cpf, np.uint32)
+        assert out.dtype == np.uint32 and out.size >= n * cpf and out.flags.c_contiguous
+        _check(self._L.sloth_render_batch(self._h, _fp(rots), n, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out[:n * cpf].reshape(n, cpf)
+
+    def render_device(self, rot: np.ndarray, device_ptr: int) -> None:
+        rot = np.ascontiguousarray(rot, np.float32).reshape(16)
+        _check(self._L.sloth_render_device(self._h, _fp(rot), C.c_void_p(device_ptr)))
+
+    def sync(self) -> None:
+        _check(self._L.sloth_ctx_sync(self._h))
+
+    def set_shader(self, thresholds=None, glyphs: bytes | None = None) -> None:
+        if thresholds is None or glyphs is None:
+            _check(self._L.sloth_shader_set(self._h, None, None))
+            return
+        thr = np.ascontiguousarray(thresholds, np.float32).reshape(9)
+        assert len(glyphs) == 10
+        _check(self._L.sloth_shader_set(self._h, _fp(thr), glyphs))
+
+    def stats_enable(self, count_fragments: bool = False, kernel_timing: bool = False) -> None:
+        _check(self._L.sloth_stats_enable(self._h, (1 if count_fragments else 0) | (2 if kernel_timing else 0)))
+
+    def stats(self) -> dict:
+        st = Stats()
+        _check(self._L.sloth_stats_get(self._h, C.byref(st)))
+        return st.as_dict()
+
+    # -- presentation (host) -----------------------------------------------------------
+    def flush(self, color: bool, webify: bool) -> bytes:
+        """Context::flush (context.rs:50-92) as bytes instead of stdout writes."""
+        return flush_bytes(self.frame_buffer, color, webify, self.image)
+
+
+def draw_mesh(context: Context, mesh: SimpleMesh, transform, shader=default_shader) -> None:
+    """rasterizer.rs:39-46.  Only ``default_shader`` (or a table set with
+    ``Context.set_shader``) can run on the device."""
+    if shader is not default_shader:
+        raise NotImplementedError("arbitrary closures cannot run on the device; use Context.set_shader(thresholds, glyphs)")
+    context._draw(mesh, transform)
+
+
+def flush_bytes(cells: np.ndarray, color: bool, webify: bool, image: bool) -> bytes:
+    """Byte-exact Context::flush (context.rs:50-92).
+
+    * no colour: every glyph, then '\\n' (println!)
+    * colour + webify: ``<span style="color:rgb(r,g,b)">c`` per cell, never closed
+    * colour: crossterm 0.18 PrintStyledContent with fg = cell colour, bg = rgb(25,25,25):
+      ``ESC[38;2;r;g;bm ESC[48;2;25;25;25m c ESC[0m`` (restated from crossterm's
+      documented behaviour: foreground first, then background, reset after; unpinned).
+    Interactive mode additionally starts with ``ESC[1;1H`` (cursor::MoveTo(0,0)).
+    """
+    cells = np.asarray(cells, np.uint32)
+    glyph = (cells & 0xFF).astype(np.uint8)
+    out = bytearray()
+    if not image:
+        out += b"\x1b[1;1H"
+    if not color:
+        out += bytes(glyph) + b"\n"
+        return bytes(out)
+    r, g, b = (cells >> 8) & 0xFF, (cells >> 16) & 0xFF, (cells >> 24) & 0xFF
+    if webify:
+        for i in range(cells.size):
+            out += b'<span style="color:rgb(%d,%d,%d)">' % (r[i], g[i], b[i])
+            out.append(glyph[i])
+    else:
+        for i in range(cells.size):
+            out += b"\x1b[38;2;%d;%d;%dm\x1b[48;2;25;25;25m" % (r[i], g[i], b[i])
+            out.append(glyph[i])
+            out += b"\x1b[0m"
+    return bytes(out)

@@ -1,0 +1,585 @@
+// capi.cu -- the C ABI of include/sloth_b200.h over the kernels in kernels.cuh.
+//
+// Host-side scalar arithmetic that the reference does once per frame stays on
+// the host, in the reference's operation order and without FMA contraction
+// (this file is compiled with -Xcompiler -ffp-contract=off):
+//   Context::update matrix        src/context.rs:104-133
+//   Rotation3::from_euler_angles  src/main.rs:76-77 (nalgebra 0.22.1)
+//   utransform * transform        src/rasterizer.rs:57 (nalgebra gemm/gemv/axcpy order)
+// There is no CPU raster fallback anywhere in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/sloth_b200.h"
+#include "kernels.cuh"
+
+using namespace sloth;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(SLOTH_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// column-major helpers (nalgebra storage): (r,c) -> m[c*4+r]
+inline float& at(float* m, int r, int c) { return m[c * 4 + r]; }
+inline float at(const float* m, int r, int c) { return m[c * 4 + r]; }
+
+// nalgebra 0.22.1 Matrix4*Matrix4: per output element, products accumulated left to right over k.
+void mat4_mul(const float* A, const float* B, float* C)
+{
+    float out[16];
+    for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i) {
+            float acc = at(A, i, 0) * at(B, 0, j);
+            for (int k = 1; k < 4; ++k) acc = acc + at(A, i, k) * at(B, k, j);
+            out[j * 4 + i] = acc;
+        }
+    std::memcpy(C, out, sizeof out);
+}
+
+const float k_default_thr[9] = {0.20f, 0.30f, 0.40f, 0.50f, 0.60f, 0.70f, 0.80f, 0.90f, 1.0f};
+const char k_default_glyph[10] = {'.', ':', '-', '=', '+', '*', '#', '%', '@', ' '};
+
+enum { EV_START = 0, EV_GEOM, EV_WALK, EV_RESOLVE_BEGIN, EV_END, EV_N };
+
+}  // namespace
+
+struct sloth_ctx {
+    int device = 0;
+    bool image = false;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    int sm_count = 148;
+
+    // scene
+    float4* sc_a = nullptr;
+    float4* sc_b = nullptr;
+    float2* sc_c = nullptr;
+    uint32_t n_tri = 0;
+    float scene_max = 0.0f;
+    bool have_scene = false;
+
+    // frame state
+    uint32_t W = 0, H = 0;
+    uint32_t row0 = 0, row1 = 0;  // band; row1 == 0 -> whole frame
+    bool sized = false;
+    unsigned long long* keys = nullptr;
+    size_t n_key_slots = 0;       // including the halo row
+    uint32_t halo_slots = 0;
+    uint32_t* d_cells[2] = {nullptr, nullptr};
+    size_t cells_per_frame = 0;
+    float* d_z = nullptr;
+    cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+
+    // queues + per-frame aux (rowbits and FrameAux are one allocation, cleared by one memset)
+    uint32_t* walk_tri = nullptr;
+    unsigned long long* walk_base = nullptr;
+    uint32_t* irr_tri = nullptr;
+    uint8_t* aux_region = nullptr;
+    size_t aux_bytes = 0, rowbits_bytes = 0;
+    uint32_t* fix_rows = nullptr;
+    uint32_t* fix_tri = nullptr;
+    uint32_t* fix_newline = nullptr;
+
+    float thr[9];
+    char glyph[10];
+
+    uint32_t stat_flags = 0;
+    uint64_t frames = 0, launches = 0;
+    cudaEvent_t ev[EV_N] = {};
+    bool ev_valid = false, ev_kernels_valid = false;
+    float batch_ms_per_frame = 0.0f;
+    bool last_was_batch = false;
+};
+
+namespace {
+
+int free_frame_state(sloth_ctx* c)
+{
+    cudaFree(c->keys);
+    cudaFree(c->d_cells[0]);
+    cudaFree(c->d_cells[1]);
+    cudaFree(c->d_z);
+    cudaFree(c->aux_region);
+    cudaFree(c->fix_rows);
+    cudaFree(c->fix_tri);
+    cudaFree(c->fix_newline);
+    c->keys = nullptr;
+    c->d_cells[0] = c->d_cells[1] = nullptr;
+    c->d_z = nullptr;
+    c->aux_region = nullptr;
+    c->fix_rows = c->fix_tri = c->fix_newline = nullptr;
+    c->sized = false;
+    return 0;
+}
+
+int alloc_frame_state(sloth_ctx* c)
+{
+    free_frame_state(c);
+    const uint32_t W = c->W, H = c->H;
+    const bool band = c->row1 != 0;
+    const uint32_t r0 = band ? c->row0 : 0, r1 = band ? c->row1 : H;
+    const uint32_t rows = r1 - r0;
+    const bool even = (W & 1u) == 0;
+    const uint32_t KW = even ? W / 2 : W;
+    c->halo_slots = (!even && r0 > 0) ? KW : 0;
+    c->n_key_slots = (size_t)rows * KW + c->halo_slots;
+    c->cells_per_frame = (size_t)rows * W + ((c->image && !band) ? H : 0);
+    CU(cudaMalloc(&c->keys, std::max<size_t>(c->n_key_slots, 1) * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(c->keys, 0xFF, std::max<size_t>(c->n_key_slots, 1) * sizeof(unsigned long long), c->stream));
+    for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->d_cells[i], (c->cells_per_frame + 2) * sizeof(uint32_t)));
+    c->rowbits_bytes = (((size_t)H + 31) / 32) * 4;
+    c->rowbits_bytes = (c->rowbits_bytes + 15) & ~(size_t)15;
+    c->aux_bytes = c->rowbits_bytes + sizeof(FrameAux);
+    CU(cudaMalloc(&c->aux_region, c->aux_bytes));
+    CU(cudaMalloc(&c->fix_rows, (size_t)H * 4 + 4));
+    CU(cudaMalloc(&c->fix_tri, (size_t)H * 4 + 4));
+    CU(cudaMalloc(&c->fix_newline, (size_t)H * 4 + 4));
+    c->sized = true;
+    return SLOTH_OK;
+}
+
+void build_params(const sloth_ctx* c, const float rot[16], FrameParams& p)
+{
+    float ut[16];
+    sloth_utransform(c->W, c->H, c->scene_max, ut);
+    float M[16];
+    mat4_mul(ut, rot, M);  // rasterizer.rs:57
+    for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 4; ++k) p.m[r * 4 + k] = at(M, r, k);
+    std::memcpy(p.thr, c->thr, sizeof p.thr);
+    std::memset(p.glyph, 0, sizeof p.glyph);
+    std::memcpy(p.glyph, c->glyph, 10);
+    p.W = c->W;
+    p.H = c->H;
+    p.wm1 = (float)(c->W - 1);
+    p.hm1 = (float)(c->H - 1);
+    const bool even = (c->W & 1u) == 0;
+    p.KW = even ? c->W / 2 : c->W;
+    p.XS = even ? 1u : 2u;
+    const bool band = c->row1 != 0;
+    p.row0 = band ? c->row0 : 0;
+    p.row1 = band ? c->row1 : c->H;
+    p.krow0 = p.row0 - (c->halo_slots ? 1u : 0u);
+    p.n_tri = c->n_tri;
+    p.image = c->image ? 1u : 0u;
+    p.count_frags = (c->stat_flags & 1u) ? 1u : 0u;
+}
+
+// Enqueue one frame on c->stream; the cells land in d_out (device).
+int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z, bool timed)
+{
+    FrameParams p;
+    build_params(c, rot, p);
+    Scene sc{c->sc_a, c->sc_b, c->sc_c};
+    Queues q;
+    q.walk_tri = c->walk_tri;
+    q.walk_base = c->walk_base;
+    q.irr_tri = c->irr_tri;
+    q.rowbits = reinterpret_cast<uint32_t*>(c->aux_region);
+    q.aux = reinterpret_cast<FrameAux*>(c->aux_region + c->rowbits_bytes);
+    q.fix_rows = c->fix_rows;
+    q.fix_tri = c->fix_tri;
+    q.fix_newline = c->fix_newline;
+    cudaStream_t st = c->stream;
+    const bool kt = timed && (c->stat_flags & 2u);
+
+    if (timed) CU(cudaEventRecord(c->ev[EV_START], st));
+    CU(cudaMemsetAsync(c->aux_region, 0, c->aux_bytes, st));
+    if (c->n_tri) {
+        k_geom<<<(c->n_tri + 255) / 256, 256, 0, st>>>(p, sc, c->keys, q);
+        if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
+        k_walk<<<c->sm_count * 8, 128, 0, st>>>(p, sc, c->keys, q);
+        k_irregular<<<c->sm_count, 256, 0, st>>>(p, sc, c->keys, q);
+        if (kt) CU(cudaEventRecord(c->ev[EV_WALK], st));
+        c->launches += 3;
+    } else if (kt) {
+        CU(cudaEventRecord(c->ev[EV_GEOM], st));
+        CU(cudaEventRecord(c->ev[EV_WALK], st));
+    }
+    const bool band = c->row1 != 0;
+    const uint32_t rows = p.row1 - p.row0;
+    const uint32_t n_tail = (c->image && !band) ? c->H : 0;
+    if (d_z) {
+        const uint32_t n = rows * c->W;
+        // z planes are only defined for whole-frame contexts (checked by the caller)
+        k_zbuffer<<<(n + 255) / 256, 256, 0, st>>>(p, c->keys, d_z, n);
+        c->launches += 1;
+    }
+    if (kt) CU(cudaEventRecord(c->ev[EV_RESOLVE_BEGIN], st));
+    if ((c->W & 1u) == 0) {
+        const uint32_t n_slots = rows * p.KW;
+        const uint32_t n = n_slots + n_tail;
+        if (n) k_resolve_even<<<(n + 255) / 256, 256, 0, st>>>(p, sc, c->keys, q, d_out, n_slots, n_tail);
+        c->launches += 1;
+    } else {
+        const uint32_t n_cells = rows * c->W;
+        const uint32_t n = n_cells + n_tail;
+        if (n) k_resolve_odd<<<(n + 255) / 256, 256, 0, st>>>(p, sc, c->keys, q, d_out, n_cells, n_tail, c->halo_slots);
+        const uint32_t nk = (uint32_t)c->n_key_slots;
+        if (nk) k_clear_keys_odd<<<(nk + 255) / 256, 256, 0, st>>>(c->keys, nk);
+        c->launches += 2;
+    }
+    if (c->image && c->n_tri) {
+        k_stampfix_scan<<<c->sm_count * 4, 256, 0, st>>>(p, sc, q);
+        k_stampfix_apply<<<1, 256, 0, st>>>(p, q, d_out);
+        c->launches += 2;
+    }
+    if (timed) CU(cudaEventRecord(c->ev[EV_END], st));
+    CU(cudaGetLastError());
+    c->frames += 1;
+    return SLOTH_OK;
+}
+
+int check_ready(sloth_ctx* c)
+{
+    if (!c) return fail(SLOTH_E_ARG, "null context");
+    if (!c->have_scene) return fail(SLOTH_E_STATE, "sloth_scene_set has not been called");
+    if (!c->sized) return fail(SLOTH_E_STATE, "sloth_ctx_resize has not been called");
+    CU(cudaSetDevice(c->device));
+    return SLOTH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sloth_last_error(void) { return g_err; }
+
+int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
+{
+    if (!out) return fail(SLOTH_E_ARG, "out is null");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(SLOTH_E_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return fail(SLOTH_E_ARG, "device %d out of range [0,%d)", device, n_dev);
+    CU(cudaSetDevice(device));
+    sloth_ctx* c = new (std::nothrow) sloth_ctx();
+    if (!c) return fail(SLOTH_E_ARG, "out of host memory");
+    c->device = device;
+    c->image = image_mode != 0;
+    std::memcpy(c->thr, k_default_thr, sizeof c->thr);
+    std::memcpy(c->glyph, k_default_glyph, sizeof c->glyph);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&c->ev_rendered[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+    }
+    *out = c;
+    return SLOTH_OK;
+}
+
+int sloth_ctx_destroy(sloth_ctx* c)
+{
+    if (!c) return SLOTH_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->copy_stream);
+    free_frame_state(c);
+    cudaFree(c->sc_a);
+    cudaFree(c->sc_b);
+    cudaFree(c->sc_c);
+    cudaFree(c->walk_tri);
+    cudaFree(c->walk_base);
+    cudaFree(c->irr_tri);
+    for (int i = 0; i < EV_N; ++i) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(c->ev_rendered[i]);
+        cudaEventDestroy(c->ev_copied[i]);
+    }
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    delete c;
+    return SLOTH_OK;
+}
+
+int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n_tri, float scene_max)
+{
+    if (!c) return fail(SLOTH_E_ARG, "null context");
+    if (n_tri && (!xyz || !rgb)) return fail(SLOTH_E_ARG, "xyz/rgb is null");
+    if (n_tri > MAX_TRIS) return fail(SLOTH_E_TOO_LARGE, "%zu triangles; the depth key holds a 27-bit index (max %u)", n_tri, MAX_TRIS);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_c);
+    cudaFree(c->walk_tri); cudaFree(c->walk_base); cudaFree(c->irr_tri);
+    c->sc_a = c->sc_b = nullptr; c->sc_c = nullptr;
+    c->walk_tri = c->irr_tri = nullptr; c->walk_base = nullptr;
+    c->have_scene = false;
+    const size_t n = n_tri ? n_tri : 1;
+    CU(cudaMalloc(&c->sc_a, n * sizeof(float4)));
+    CU(cudaMalloc(&c->sc_b, n * sizeof(float4)));
+    CU(cudaMalloc(&c->sc_c, n * sizeof(float2)));
+    CU(cudaMalloc(&c->walk_tri, n * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->walk_base, n * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->irr_tri, n * sizeof(uint32_t)));
+    if (n_tri) {
+        float* d_xyz = nullptr;
+        uint8_t* d_rgb = nullptr;
+        CU(cudaMalloc(&d_xyz, n_tri * 9 * sizeof(float)));
+        CU(cudaMalloc(&d_rgb, n_tri * 3));
+        CU(cudaMemcpyAsync(d_xyz, xyz, n_tri * 9 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_rgb, rgb, n_tri * 3, cudaMemcpyHostToDevice, c->stream));
+        k_pack_scene<<<(unsigned)((n_tri + 255) / 256), 256, 0, c->stream>>>(d_xyz, d_rgb, (uint32_t)n_tri, c->sc_a, c->sc_b, c->sc_c);
+        c->launches += 1;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(d_xyz);
+        cudaFree(d_rgb);
+    }
+    c->n_tri = (uint32_t)n_tri;
+    c->scene_max = scene_max;
+    c->have_scene = true;
+    return SLOTH_OK;
+}
+
+int sloth_ctx_resize(sloth_ctx* c, uint32_t W, uint32_t H)
+{
+    if (!c) return fail(SLOTH_E_ARG, "null context");
+    if (W == 0 || H == 0) return fail(SLOTH_E_ARG, "width and height must be >= 1 (got %ux%u)", W, H);
+    if (W > 65535u || H > 65535u)
+        return fail(SLOTH_E_TOO_LARGE, "width/height above 65535 (the reference takes the size `as u16`, context.rs:99)");
+    if ((unsigned long long)W * H + H >= (1ull << 31)) return fail(SLOTH_E_TOO_LARGE, "W*H+H must stay below 2^31");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    c->W = W;
+    c->H = H;
+    c->row0 = c->row1 = 0;
+    return alloc_frame_state(c);
+}
+
+int sloth_ctx_set_band(sloth_ctx* c, uint32_t row0, uint32_t row1)
+{
+    if (!c) return fail(SLOTH_E_ARG, "null context");
+    if (c->W == 0) return fail(SLOTH_E_STATE, "sloth_ctx_resize has not been called");
+    if (!(row0 == 0 && row1 == 0) && (row0 >= row1 || row1 > c->H))
+        return fail(SLOTH_E_ARG, "band [%u,%u) is not inside [0,%u)", row0, row1, c->H);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    c->row0 = row0;
+    c->row1 = row1;
+    return alloc_frame_state(c);
+}
+
+size_t sloth_cells_per_frame(const sloth_ctx* c) { return c ? c->cells_per_frame : 0; }
+
+int sloth_render(sloth_ctx* c, const float rot[16], uint32_t* cells_out, float* z_out)
+{
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (!rot || !cells_out) return fail(SLOTH_E_ARG, "rot/cells_out is null");
+    if (z_out && c->row1 != 0) return fail(SLOTH_E_ARG, "z_out is not available in band mode");
+    if (z_out && !c->d_z) CU(cudaMalloc(&c->d_z, (size_t)c->W * c->H * sizeof(float)));
+    rc = enqueue_frame(c, rot, c->d_cells[0], z_out ? c->d_z : nullptr, true);
+    if (rc) return rc;
+    c->ev_valid = true;
+    c->ev_kernels_valid = (c->stat_flags & 2u) != 0;
+    c->last_was_batch = false;
+    CU(cudaMemcpyAsync(cells_out, c->d_cells[0], c->cells_per_frame * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (z_out)
+        CU(cudaMemcpyAsync(z_out, c->d_z, (size_t)c->W * c->H * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SLOTH_OK;
+}
+
+int sloth_render_device(sloth_ctx* c, const float rot[16], void* d_cells)
+{
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (!rot || !d_cells) return fail(SLOTH_E_ARG, "rot/d_cells is null");
+    if (((uintptr_t)d_cells & 7u) != 0) return fail(SLOTH_E_ARG, "d_cells must be 8-byte aligned");
+    rc = enqueue_frame(c, rot, static_cast<uint32_t*>(d_cells), nullptr, true);
+    if (rc) return rc;
+    c->ev_valid = true;
+    c->ev_kernels_valid = (c->stat_flags & 2u) != 0;
+    c->last_was_batch = false;
+    return SLOTH_OK;
+}
+
+int sloth_ctx_sync(sloth_ctx* c)
+{
+    if (!c) return fail(SLOTH_E_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    return SLOTH_OK;
+}
+
+int sloth_render_batch(sloth_ctx* c, const float* rots, size_t n_frames, uint32_t* cells_out)
+{
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (n_frames == 0) return SLOTH_OK;
+    if (!rots || !cells_out) return fail(SLOTH_E_ARG, "rots/cells_out is null");
+    const size_t cpf = c->cells_per_frame;
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    for (size_t k = 0; k < n_frames; ++k) {
+        const int b = (int)(k & 1);
+        if (k >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));  // buffer b is free again
+        rc = enqueue_frame(c, rots + 16 * k, c->d_cells[b], nullptr, false);
+        if (rc) return rc;
+        CU(cudaEventRecord(c->ev_rendered[b], c->stream));
+        CU(cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[b], 0));
+        CU(cudaMemcpyAsync(cells_out + k * cpf, c->d_cells[b], cpf * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    }
+    CU(cudaEventRecord(c->ev[EV_END], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, c->ev[EV_START], c->ev[EV_END]));
+    c->batch_ms_per_frame = ms / (float)n_frames;
+    c->last_was_batch = true;
+    c->ev_valid = true;
+    c->ev_kernels_valid = false;
+    return SLOTH_OK;
+}
+
+int sloth_shader_set(sloth_ctx* c, const float thr[9], const char glyph[10])
+{
+    if (!c) return fail(SLOTH_E_ARG, "null context");
+    if (!thr || !glyph) {
+        std::memcpy(c->thr, k_default_thr, sizeof c->thr);
+        std::memcpy(c->glyph, k_default_glyph, sizeof c->glyph);
+        return SLOTH_OK;
+    }
+    std::memcpy(c->thr, thr, sizeof c->thr);
+    std::memcpy(c->glyph, glyph, 10);
+    return SLOTH_OK;
+}
+
+int sloth_stats_enable(sloth_ctx* c, uint32_t flags)
+{
+    if (!c) return fail(SLOTH_E_ARG, "null context");
+    c->stat_flags = flags;
+    return SLOTH_OK;
+}
+
+int sloth_stats_get(sloth_ctx* c, sloth_stats* out)
+{
+    if (!c || !out) return fail(SLOTH_E_ARG, "null argument");
+    std::memset(out, 0, sizeof *out);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    out->frames = c->frames;
+    out->kernel_launches = c->launches;
+    out->n_tri = c->n_tri;
+    if (c->sized && c->aux_region) {
+        FrameAux aux;
+        CU(cudaMemcpy(&aux, c->aux_region + c->rowbits_bytes, sizeof aux, cudaMemcpyDeviceToHost));
+        out->fragments = aux.frag_counter;
+        out->walk_tris = (uint32_t)(aux.walk_counter >> ITEM_BITS);
+        out->walk_items = (uint32_t)(aux.walk_counter & ITEM_MASK);
+        out->irregular_tris = aux.irr_count;
+        out->stamp_fixups = aux.fix_count;
+    }
+    if (c->ev_valid) {
+        if (c->last_was_batch) out->last_frame_ms = c->batch_ms_per_frame;
+        else CU(cudaEventElapsedTime(&out->last_frame_ms, c->ev[EV_START], c->ev[EV_END]));
+        if (c->ev_kernels_valid && !c->last_was_batch) {
+            CU(cudaEventElapsedTime(&out->geom_ms, c->ev[EV_START], c->ev[EV_GEOM]));
+            CU(cudaEventElapsedTime(&out->walk_ms, c->ev[EV_GEOM], c->ev[EV_WALK]));
+            CU(cudaEventElapsedTime(&out->resolve_ms, c->ev[EV_RESOLVE_BEGIN], c->ev[EV_END]));
+        }
+    }
+    return SLOTH_OK;
+}
+
+int sloth_pinned_alloc(size_t bytes, void** out)
+{
+    if (!out) return fail(SLOTH_E_ARG, "out is null");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SLOTH_OK;
+}
+
+int sloth_pinned_free(void* ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
+    return SLOTH_OK;
+}
+
+/* ---- host-side helpers ---- */
+
+void sloth_utransform(uint32_t W, uint32_t H, float scene_max, float out[16])
+{
+    // Context::blank starts from identity (context.rs:25-27); update() only
+    // replaces it when the u16 size differs from (0,0) (context.rs:104).
+    std::memset(out, 0, 16 * sizeof(float));
+    at(out, 0, 0) = at(out, 1, 1) = at(out, 2, 2) = at(out, 3, 3) = 1.0f;
+    const uint16_t w16 = (uint16_t)W, h16 = (uint16_t)H;
+    if (w16 == 0 && h16 == 0) return;
+    const float fw = (float)w16, fh = (float)h16;
+    const float scale = std::fmin(fh, fw / 2.0f) / scene_max / 2.0f;  // context.rs:114
+    at(out, 0, 0) = scale;
+    at(out, 0, 3) = fw / 4.0f;
+    at(out, 1, 1) = -scale;
+    at(out, 1, 3) = fh / 2.0f;
+    at(out, 2, 2) = scale;
+}
+
+void sloth_rotation_from_euler(float roll, float pitch, float yaw, float out[16])
+{
+    const float sr = sinf(roll), cr = cosf(roll);
+    const float sp = sinf(pitch), cp = cosf(pitch);
+    const float sy = sinf(yaw), cy = cosf(yaw);
+    std::memset(out, 0, 16 * sizeof(float));
+    at(out, 0, 0) = cy * cp;
+    at(out, 0, 1) = cy * sp * sr - sy * cr;
+    at(out, 0, 2) = cy * sp * cr + sy * sr;
+    at(out, 1, 0) = sy * cp;
+    at(out, 1, 1) = sy * sp * sr + cy * cr;
+    at(out, 1, 2) = sy * sp * cr - cy * sr;
+    at(out, 2, 0) = -sp;
+    at(out, 2, 1) = cp * sr;
+    at(out, 2, 2) = cp * cr;
+    at(out, 3, 3) = 1.0f;
+}
+
+size_t sloth_turntable_pitches(float y_arg, uint32_t n_frames, float* out, size_t cap)
+{
+    const float pi = 3.14159265358979323846f;
+    float pitch = y_arg;
+    pitch += pi;                                           // inputs.rs:148
+    const float step = (2.0f * pi) * (1.0f / (float)n_frames);  // main.rs:57
+    size_t count = 0;
+    long long frame_count = 0;
+    for (;;) {
+        if (out && count < cap) out[count] = pitch;
+        ++count;
+        pitch += step;                                     // main.rs:92-96
+        if (pitch > 9.42477f || (long long)n_frames - 1 == frame_count) break;  // main.rs:99
+        ++frame_count;
+    }
+    return count;
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle, bit for bit
+(cells: glyph + colour of every terminal cell; z-buffer: every depth winner)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+import rust_sloth_b200 as rs
+from rust_sloth_b200 import meshes
+import scenes as S
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_frame(xyz, rgb, s0, W, H, rot, image=True, want_z=True, band=None):
+    ctx = rs.Context.blank(image)
+    try:
+        ctx.set_scene(xyz, rgb, s0)
+        ctx.resize(W, H)
+        if band:
+            ctx.set_band(*band)
+        ctx.stats_enable(count_fragments=True)
+        cells, z = ctx.render(rot, want_z=want_z and not band)
+        return cells, z, ctx.stats()
+    finally:
+        ctx.close()
+
+
+def assert_same(cells, z, ocells, oz, what):
+    bad = np.flatnonzero(cells != ocells)
+    assert bad.size == 0, f"{what}: {bad.size} cells differ, first at {bad[:8]}: gpu={cells[bad[:8]]} oracle={ocells[bad[:8]]}"
+    if z is not None:
+        badz = np.flatnonzero(z.view(np.uint32) != np.where(oz == 0, np.float32(0), oz).view(np.uint32))
+        assert badz.size == 0, f"{what}: {badz.size} z values differ, first at {badz[:8]}"
+
+
+@pytest.mark.parametrize("case", S.golden()["cases"], ids=lambda c: f"{c['scene']}-{c['W']}x{c['H']}")
+def test_bundled_models_match_oracle_and_golden(case):
+    xyz, rgb, s0 = S.soup(case["scene"])
+    rot = oracle.rotation(case["roll"], case["pitch"], case["yaw"])
+    ocells, oz, ocnt = oracle.render(xyz, rgb, s0, case["W"], case["H"], rot, image=True, mode=0)
+    assert hashlib.sha256(ocells.tobytes()).hexdigest() == case["cells_sha256"]
+    cells, z, st = gpu_frame(xyz, rgb, s0, case["W"], case["H"], rot)
+    assert_same(cells, z, ocells, oz, str(case["scene"]))
+    assert hashlib.sha256(cells.tobytes()).hexdigest() == case["cells_sha256"]
+    assert st["fragments"] == ocnt["covered"]
+
+
+@pytest.mark.parametrize("image", [True, False])
+@pytest.mark.parametrize("kind", ["uniform", "small", "sliver", "collinear", "dup", "axis"])
+def test_fuzz_soups(kind, image):
+    sizes = [(7, 7), (8, 9), (33, 20), (64, 64), (101, 57), (160, 80), (199, 200), (2, 2), (3, 1), (1, 5)]
+    for seed in range(40):
+        n = 1 + (seed * 7) % 64
+        xyz, rgb, s0 = meshes.random_soup(seed, n, kind=kind)
+        W, H = sizes[seed % len(sizes)]
+        rot = oracle.rotation(0.1 * seed, np.float32(np.pi) + 0.37 * seed, 0.05 * seed)
+        ocells, oz, _ = oracle.render(xyz, rgb, s0, W, H, rot, image=image, mode=0)
+        cells, z, _ = gpu_frame(xyz, rgb, s0, W, H, rot, image=image)
+        assert_same(cells, z, ocells, oz, f"{kind} seed={seed} n={n} {W}x{H} image={image}")
+
+
+def test_non_finite_and_huge_coordinates():
+    xyz, rgb, s0 = meshes.random_soup(3, 24)
+    xyz = xyz.copy()
+    xyz[1, 2] = np.nan
+    xyz[2, 0] = np.inf
+    xyz[3, 4] = -np.inf
+    xyz[4] *= np.float32(1e30)
+    xyz[5, 8] = np.nan
+    xyz[6, 5] = np.float32(3e38)
+    rot = oracle.rotation(0.2, 3.0, 0.1)
+    for (W, H) in [(40, 20), (41, 21)]:
+        ocells, oz, _ = oracle.render(xyz, rgb, s0, W, H, rot, mode=0)
+        cells, z, st = gpu_frame(xyz, rgb, s0, W, H, rot)
+        assert st["irregular_tris"] > 0
+        assert_same(cells, z, ocells, oz, f"nonfinite {W}x{H}")
+
+
+def test_degenerate_scene_scale():
+    xyz, rgb, _ = meshes.random_soup(5, 16)
+    rot = oracle.rotation(0.0, 3.0, 0.0)
+    for s0 in [0.0, np.inf, np.nan, 1e-30]:
+        ocells, oz, _ = oracle.render(xyz, rgb, s0, 30, 20, rot, mode=0)
+        cells, z, _ = gpu_frame(xyz, rgb, s0, 30, 20, rot)
+        assert_same(cells, z, ocells, oz, f"scale0={s0}")
+
+
+def test_empty_scene_and_tiny_frames():
+    rot = oracle.rotation(0.0, 3.0, 0.0)
+    e_xyz, e_rgb = np.zeros((0, 9), np.float32), np.zeros((0, 3), np.uint8)
+    for (W, H) in [(1, 1), (2, 3), (80, 40)]:
+        ocells, oz, _ = oracle.render(e_xyz, e_rgb, 1.0, W, H, rot)
+        cells, z, _ = gpu_frame(e_xyz, e_rgb, 1.0, W, H, rot)
+        assert_same(cells, z, ocells, oz, f"empty {W}x{H}")
+
+
+def test_icosphere_small_frequencies():
+    for f, (W, H) in [(4, (80, 40)), (24, (160, 80)), (64, (320, 200))]:
+        xyz, rgb, s0 = meshes.icosphere(f)
+        for k in range(3):
+            rot = oracle.rotation(0.0, np.float32(np.pi) + 0.5 * k, 0.0)
+            ocells, oz, ocnt = oracle.render(xyz, rgb, s0, W, H, rot, mode=0)
+            cells, z, st = gpu_frame(xyz, rgb, s0, W, H, rot)
+            assert_same(cells, z, ocells, oz, f"icosphere f={f}")
+            assert st["fragments"] == ocnt["covered"]
+
+
+def test_custom_shader_table():
+    xyz, rgb, s0 = S.soup("suzy")
+    rot = oracle.rotation(0.0, S.PI, 0.0)
+    thr = np.array([0.1, 0.15, 0.35, 0.5, 0.55, 0.6, 0.85, 0.95, 2.0], np.float32)
+    gl = b"abcdefghi?"
+    ocells, oz, _ = oracle.render(xyz, rgb, s0, 120, 60, rot, thr=thr, glyph=gl)
+    ctx = rs.Context.blank(True)
+    ctx.set_scene(xyz, rgb, s0)
+    ctx.resize(120, 60)
+    ctx.set_shader(thr, gl)
+    cells, z = ctx.render(rot, want_z=True)
+    ctx.close()
+    assert_same(cells, z, ocells, oz, "custom shader")
+
+
+def test_row_bands_reassemble_to_the_whole_frame():
+    xyz, rgb, s0 = S.soup("pikachu")
+    pitches = oracle.turntable(0.0, 360)
+    for (W, H, nb) in [(160, 80, 4), (161, 83, 3), (80, 40, 8)]:
+        rot = oracle.rotation(0.0, pitches[144], 0.0)  # a frame with row wrap
+        ocells, _, _ = oracle.render(xyz, rgb, s0, W, H, rot, mode=0)
+        parts = []
+        edges = [H * i // nb for i in range(nb + 1)]
+        for i in range(nb):
+            cells, _, _ = gpu_frame(xyz, rgb, s0, W, H, rot, band=(edges[i], edges[i + 1]))
+            assert cells.size == (edges[i + 1] - edges[i]) * W
+            parts.append(cells)
+        whole = np.concatenate(parts + [np.full(H, ord(" "), np.uint32)])
+        bad = np.flatnonzero(whole != ocells)
+        assert bad.size == 0, f"bands {W}x{H}/{nb}: {bad.size} cells differ, first {bad[:8]}"
+
+
+def test_batch_equals_single_frames_and_is_deterministic():
+    xyz, rgb, s0 = S.soup("pikachu")
+    pitches = oracle.turntable(0.0, 12)
+    rots = np.stack([oracle.rotation(0.0, p, 0.0) for p in pitches])
+    ctx = rs.Context.blank(True)
+    ctx.set_scene(xyz, rgb, s0)
+    ctx.resize(200, 100)
+    a = ctx.render_batch(rots).copy()
+    b = ctx.render_batch(rots).copy()
+    assert np.array_equal(a, b)
+    for k in range(len(pitches)):
+        ocells, _, _ = oracle.render(xyz, rgb, s0, 200, 100, rots[k], mode=1)
+        assert np.array_equal(a[k], ocells), f"frame {k}"
+    ctx.close()
+
+
+def test_reference_style_host_api():
+    """Reads like the reference's main loop (main.rs:76-89)."""
+    xyz, rgb, s0 = S.soup("pikachu")
+    sizes = S.mesh_sizes("pikachu")
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    mesh_queue = [rs.SimpleMesh(xyz[offs[i]:offs[i + 1]], rgb[offs[i]:offs[i + 1]]) for i in range(len(sizes))]
+    context = rs.Context.blank(True)
+    context.width, context.height = 80, 40            # match_dimensions
+    rot = rs.rotation_from_euler(0.0, S.PI, 0.0)
+    context.update((0, 0), mesh_queue)
+    context.clear()
+    for mesh in mesh_queue:
+        rs.draw_mesh(context, mesh, rot, rs.default_shader)
+    text = context.flush(False, False).decode("latin-1")
+    gold = [c for c in S.golden()["cases"] if c["scene"] == "pikachu" and c["W"] == 80][0]
+    assert text == gold["text"] + "\n"
+    context.close()
