@@ -87,6 +87,9 @@ SLOTH_API int sloth_render_batch(sloth_ctx *ctx, const float *rots, size_t n_fra
  * Runs on the context's stream; sloth_ctx_sync() waits for it. */
 SLOTH_API int sloth_render_device(sloth_ctx *ctx, const float rot[16], void *d_cells);
 SLOTH_API int sloth_ctx_sync(sloth_ctx *ctx);
+/* The CUDA stream (cudaStream_t) every kernel of this context is launched on, so
+ * a caller can record its own events around sloth_render_device calls. */
+SLOTH_API void *sloth_ctx_stream(sloth_ctx *ctx);
 
 /*
  * Row-band mode for one huge frame split across GPUs: this context produces

@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "sloth_render_batch", "sloth_render_device", "sloth_ctx_sync", "sloth_ctx_set_band",
     "sloth_shader_set", "sloth_stats_get", "sloth_stats_enable", "sloth_last_error",
     "sloth_rotation_from_euler", "sloth_utransform", "sloth_turntable_pitches", "sloth_cells_per_frame",
-    "sloth_pinned_alloc", "sloth_pinned_free",
+    "sloth_pinned_alloc", "sloth_pinned_free", "sloth_ctx_stream",
 ]
 
 
@@ -91,6 +91,8 @@ def load_library() -> C.CDLL:
     L.sloth_render_batch.argtypes = [vp, fp, C.c_size_t, C.POINTER(C.c_uint32)]
     L.sloth_render_device.argtypes = [vp, fp, vp]
     L.sloth_ctx_sync.argtypes = [vp]
+    L.sloth_ctx_stream.argtypes = [vp]
+    L.sloth_ctx_stream.restype = vp
     L.sloth_ctx_set_band.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.sloth_shader_set.argtypes = [vp, fp, C.c_char_p]
     L.sloth_stats_get.argtypes = [vp, C.POINTER(Stats)]
@@ -389,6 +391,10 @@ class Context:
     def render_device(self, rot: np.ndarray, device_ptr: int) -> None:
         rot = np.ascontiguousarray(rot, np.float32).reshape(16)
         _check(self._L.sloth_render_device(self._h, _fp(rot), C.c_void_p(device_ptr)))
+
+    def stream_ptr(self) -> int:
+        """cudaStream_t of this context (for torch.cuda.ExternalStream / event timing)."""
+        return int(self._L.sloth_ctx_stream(self._h) or 0)
 
     def sync(self) -> None:
         _check(self._L.sloth_ctx_sync(self._h))

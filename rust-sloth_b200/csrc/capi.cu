@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -95,6 +96,10 @@ struct sloth_ctx {
     uint32_t* walk_tri = nullptr;
     unsigned long long* walk_base = nullptr;
     uint32_t* irr_tri = nullptr;
+    uint32_t* tile_hull = nullptr;   // [ceil(n_tri/256)] row hull of each geometry tile
+    int geom_variant = 3;            // SLOTH_GEOM=1 selects the first-generation kernel k_geom (A/B runs)
+    uint32_t debug = 0;              // SLOTH_DEBUG bits, profiling experiments only
+    bool scene_clean = false;        // every |coordinate| <= 2^20: no per-triangle regularity test needed
     uint8_t* aux_region = nullptr;
     size_t aux_bytes = 0, rowbits_bytes = 0;
     uint32_t* fix_rows = nullptr;
@@ -149,7 +154,7 @@ int alloc_frame_state(sloth_ctx* c)
     CU(cudaMemsetAsync(c->keys, 0xFF, std::max<size_t>(c->n_key_slots, 1) * sizeof(unsigned long long), c->stream));
     for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->d_cells[i], (c->cells_per_frame + 2) * sizeof(uint32_t)));
     c->rowbits_bytes = (((size_t)H + 31) / 32) * 4;
-    c->rowbits_bytes = (c->rowbits_bytes + 15) & ~(size_t)15;
+    c->rowbits_bytes = (c->rowbits_bytes + 8 + 15) & ~(size_t)15;   // + one padding word for the 2-word probe
     c->aux_bytes = c->rowbits_bytes + sizeof(FrameAux);
     CU(cudaMalloc(&c->aux_region, c->aux_bytes));
     CU(cudaMalloc(&c->fix_rows, (size_t)H * 4 + 4));
@@ -184,6 +189,7 @@ void build_params(const sloth_ctx* c, const float rot[16], FrameParams& p)
     p.n_tri = c->n_tri;
     p.image = c->image ? 1u : 0u;
     p.count_frags = (c->stat_flags & 1u) ? 1u : 0u;
+    p.debug = c->debug;
 }
 
 // Enqueue one frame on c->stream; the cells land in d_out (device).
@@ -207,7 +213,19 @@ int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z
     if (timed) CU(cudaEventRecord(c->ev[EV_START], st));
     CU(cudaMemsetAsync(c->aux_region, 0, c->aux_bytes, st));
     if (c->n_tri) {
-        k_geom<<<(c->n_tri + 255) / 256, 256, 0, st>>>(p, sc, c->keys, q);
+        if (c->geom_variant == 1) {
+            k_geom<<<(c->n_tri + 255) / 256, 256, 0, st>>>(p, sc, c->keys, q);
+        } else {
+            const uint32_t n_chunks = (c->n_tri + 31) / 32;
+            const uint32_t n_batches = (n_chunks + G3_BATCH - 1) / G3_BATCH;
+            const uint32_t grid = std::min<uint32_t>((n_batches + G3_WARPS - 1) / G3_WARPS, (uint32_t)c->sm_count * 3u);
+            // a clean scene under a bounded matrix cannot produce |x'|,|y'| > 2^40: skip the per-triangle test
+            bool bounded = c->scene_clean;
+            for (int i = 0; i < 8; ++i) bounded = bounded && std::fabs(p.m[i]) <= 131072.0f;
+            const size_t dyn = (((size_t)c->H + 31) / 32 + 1) * sizeof(uint32_t);   // per-block row-stamp bitmap
+            if (bounded) k_geom3<false><<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->keys, q, c->tile_hull);
+            else k_geom3<true><<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->keys, q, c->tile_hull);
+        }
         if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
         k_walk<<<c->sm_count * 8, 128, 0, st>>>(p, sc, c->keys, q);
         k_irregular<<<c->sm_count, 256, 0, st>>>(p, sc, c->keys, q);
@@ -241,7 +259,7 @@ int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z
         c->launches += 2;
     }
     if (c->image && c->n_tri) {
-        k_stampfix_scan<<<c->sm_count * 4, 256, 0, st>>>(p, sc, q);
+        k_stampfix_scan<<<c->sm_count * 4, 256, 0, st>>>(p, sc, q, c->tile_hull, c->geom_variant == 1 ? 0u : 1u, c->geom_variant == 1 ? GEOM_TILE : 32u);
         k_stampfix_apply<<<1, 256, 0, st>>>(p, q, d_out);
         c->launches += 2;
     }
@@ -286,6 +304,11 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    if (const char* g = std::getenv("SLOTH_DEBUG")) c->debug = (uint32_t)std::atoi(g);
+    if (const char* g = std::getenv("SLOTH_GEOM")) {
+        const int v = std::atoi(g);
+        if (v == 1) c->geom_variant = 1;
+    }
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
@@ -310,6 +333,7 @@ int sloth_ctx_destroy(sloth_ctx* c)
     cudaFree(c->walk_tri);
     cudaFree(c->walk_base);
     cudaFree(c->irr_tri);
+    cudaFree(c->tile_hull);
     for (int i = 0; i < EV_N; ++i) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) {
         cudaEventDestroy(c->ev_rendered[i]);
@@ -329,7 +353,8 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_c);
-    cudaFree(c->walk_tri); cudaFree(c->walk_base); cudaFree(c->irr_tri);
+    cudaFree(c->walk_tri); cudaFree(c->walk_base); cudaFree(c->irr_tri); cudaFree(c->tile_hull);
+    c->tile_hull = nullptr;
     c->sc_a = c->sc_b = nullptr; c->sc_c = nullptr;
     c->walk_tri = c->irr_tri = nullptr; c->walk_base = nullptr;
     c->have_scene = false;
@@ -340,6 +365,7 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
     CU(cudaMalloc(&c->walk_tri, n * sizeof(uint32_t)));
     CU(cudaMalloc(&c->walk_base, n * sizeof(unsigned long long)));
     CU(cudaMalloc(&c->irr_tri, n * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->tile_hull, ((n + 31) / 32) * sizeof(uint32_t)));
     if (n_tri) {
         float* d_xyz = nullptr;
         uint8_t* d_rgb = nullptr;
@@ -353,6 +379,11 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
         CU(cudaStreamSynchronize(c->stream));
         cudaFree(d_xyz);
         cudaFree(d_rgb);
+    }
+    {   // finite and |v| <= 2^20 everywhere?  (NaN fails the comparison)
+        bool clean = true;
+        for (size_t i = 0; i < n_tri * 9 && clean; ++i) clean = std::fabs(xyz[i]) <= 1048576.0f;
+        c->scene_clean = clean;
     }
     c->n_tri = (uint32_t)n_tri;
     c->scene_max = scene_max;
@@ -424,6 +455,8 @@ int sloth_render_device(sloth_ctx* c, const float rot[16], void* d_cells)
     c->last_was_batch = false;
     return SLOTH_OK;
 }
+
+void* sloth_ctx_stream(sloth_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int sloth_ctx_sync(sloth_ctx* c)
 {

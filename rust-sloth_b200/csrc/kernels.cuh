@@ -152,6 +152,313 @@ __global__ void __launch_bounds__(256) k_geom(const __grid_constant__ FrameParam
     }
 }
 
+SLOTH_DEV uint32_t row_mask_in_word(uint32_t y0, uint32_t y1, uint32_t w)
+{
+    const uint32_t lo = max(y0, w << 5), hi = min(y1, (w + 1u) << 5);
+    if (lo >= hi) return 0u;
+    return (0xFFFFFFFFu >> (32u - (hi - lo))) << (lo & 31u);
+}
+
+static constexpr uint32_t GEOM_TILE = 256;   // triangles per block of the first-generation kernel
+
+// ---------------------------------------------------------------------------------
+// k_geom3: the geometry kernel, warp-autonomous (no block barriers).
+//
+// Persistent warps walk the triangle stream in batches of 16 consecutive chunks of
+// 32 triangles (lane = triangle):
+//   A  prefetched 16+16+8 B loads, x'/y' transform (z' is not needed unless a
+//      fragment is found), bounds, row stamps, classification.
+//   cull  a triangle whose computed orientation is negative by more than the
+//      rounding slack of the edge functions cannot cover any candidate (proof at
+//      backface_proven); closed meshes lose half their triangles here, and whole
+//      warps skip phase B.
+//   B  every remaining triangle whose scan domain fits 2 rows x (2 columns + 1
+//      closing column) is evaluated in registers, all lanes in lockstep: the edge
+//      functions are separable, w_i(x,y) = c_i(y) - g_i(x), so the 6 candidates
+//      cost 2x3 row terms + 3x3 column terms + 18 subtractions.  Nothing can be
+//      covered right of a column where a closing edge already fails (row_closed);
+//      if that cannot be shown inside the footprint the triangle goes to k_walk.
+//   C  covering triangles are parked in a per-warp shared-memory queue, one entry
+//      per fragment; when >= 64 fragments are queued they are emitted with all
+//      lanes busy: re-transform (now with z'), normal, depth, glyph, 64-bit
+//      atomicMin into the key plane.
+// ---------------------------------------------------------------------------------
+static constexpr uint32_t G3_WARPS = 8;          // warps per block
+static constexpr uint32_t G3_BATCH = 16;         // consecutive chunks per warp turn
+static constexpr uint32_t G3_TRI_CAP = 96;       // queued covering triangles per warp
+static constexpr uint32_t G3_FRAG_CAP = 256;     // queued fragments per warp (64 + 32*6)
+static constexpr uint32_t G3_FLUSH = 64;
+
+struct G3Queue {
+    float raw[9][G3_TRI_CAP];     // object-space vertices
+    uint32_t tri[G3_TRI_CAP];
+    uint32_t xy[G3_TRI_CAP];      // minx | miny << 16
+    uint16_t frag[G3_FRAG_CAP];   // queue slot | footprint bit << 8   (bit = row*3 + col)
+};
+
+// No candidate of the scan domain can pass all three edge tests when the computed
+// orientation A_c = fl(fl(dy2*dx1) - fl(dx2*dy1)) (bit-identical to the reference's
+// orient(v1,v2,v3)) satisfies  A_c < -2^-18 * L * D,  L = larger bbox side,
+// D = largest |candidate - vertex| distance along an axis.  Proof sketch (u = 2^-24,
+// regular triangle, DESIGN.md has the full argument): each computed edge value has
+// the sign of E1(1+t1) - E2(1+t2) with |t| <= 3.01u, so "all three >= 0" implies
+// A_exact >= -3.01u * sum(|E1|+|E2|) >= -18.1u L D, while A_exact <= A_c(1-u) + 6.1u L^2
+// and L <= 2D; 2^-18 = 64u leaves a factor > 2 for the rounding of the bound itself.
+SLOTH_DEV bool backface_proven(const FrameParams& p, float dx1, float dy1, float dx2, float dy2, float mn0,
+                               float mx0, float mn1, float mx1)
+{
+    const float area = sub(mul(dy2, dx1), mul(dx2, dy1));
+    const float L = fmaxf(sub(mx0, mn0), sub(mx1, mn1));
+    const float D = fmaxf(add(fmaxf(fabsf(mn0), fabsf(mx0)), p.wm1), add(fmaxf(fabsf(mn1), fabsf(mx1)), p.hm1));
+    const float T = mul(mul(L, D), 3.814697265625e-06f);   // 2^-18 L D
+    // T > 1e-30 keeps the bound itself (and the edge products it stands for) out of the
+    // denormal range, where the relative-error argument would not hold.
+    return T > 1e-30f && area < -T;
+}
+
+SLOTH_DEV void g3_emit_all(const FrameParams& p, const G3Queue& wq, uint32_t n_fq, uint32_t lane,
+                           unsigned long long* __restrict__ keys, uint32_t& nfrag_count)
+{
+    for (uint32_t f = lane; f < n_fq; f += 32u) {
+        const uint32_t e = wq.frag[f], slot = e & 255u, bit = e >> 8;
+        float v[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] = wq.raw[k][slot];
+        // same operations on the same inputs as phase A: bit-identical x', y'
+        Setup s;
+        s.x1 = xform_row(p.m + 0, v[0], v[1], v[2]); s.y1 = xform_row(p.m + 4, v[0], v[1], v[2]);
+        s.z1 = xform_row(p.m + 8, v[0], v[1], v[2]);
+        s.x2 = xform_row(p.m + 0, v[3], v[4], v[5]); s.y2 = xform_row(p.m + 4, v[3], v[4], v[5]);
+        s.z2 = xform_row(p.m + 8, v[3], v[4], v[5]);
+        s.x3 = xform_row(p.m + 0, v[6], v[7], v[8]); s.y3 = xform_row(p.m + 4, v[6], v[7], v[8]);
+        s.z3 = xform_row(p.m + 8, v[6], v[7], v[8]);
+        s.dx0 = sub(s.x3, s.x2); s.dy0 = sub(s.y3, s.y2);
+        s.dx1 = sub(s.x1, s.x3); s.dy1 = sub(s.y1, s.y3);
+        s.dx2 = sub(s.x2, s.x1); s.dy2 = sub(s.y2, s.y1);
+        const uint32_t xy = wq.xy[slot];
+        const uint32_t x = (xy & 0xFFFFu) + (bit >= 3u ? bit - 3u : bit), y = (xy >> 16) + (bit >= 3u ? 1u : 0u);
+        const RowC rc = row_setup(s, y);
+        float w0, w1, w2;
+        edge_eval(s, rc, x, w0, w1, w2);
+        Shade sh;
+        shade_setup(s, sh);
+        emit_fragment(p, s, sh, wq.tri[slot], x, y, w0, w1, w2, keys);
+        ++nfrag_count;
+    }
+}
+
+template <bool CHECK_REGULAR>
+__global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constant__ FrameParams p, const Scene sc,
+                                                            unsigned long long* __restrict__ keys, const Queues q,
+                                                            uint32_t* __restrict__ chunk_hull)
+{
+    __shared__ G3Queue queues[G3_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    G3Queue& wq = queues[warp];
+    const uint32_t n_chunks = (p.n_tri + 31u) >> 5;
+    const uint32_t n_batches = (n_chunks + G3_BATCH - 1u) / G3_BATCH;
+    const uint32_t n_warps = gridDim.x * G3_WARPS;
+    uint32_t n_tq = 0, n_fq = 0, nfrag_count = 0;
+    const bool do_stamps = p.image && !(p.debug & 2u);
+    extern __shared__ uint32_t s_rowbits[];   // (H+31)/32 + 1 words: rows stamped by this block
+    const uint32_t n_row_words = ((p.H + 31u) >> 5) + 1u;
+    if (do_stamps) {
+        for (uint32_t i = threadIdx.x; i < n_row_words; i += blockDim.x) s_rowbits[i] = 0u;
+        __syncthreads();
+    }
+
+    uint32_t batch = blockIdx.x * G3_WARPS + warp;
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
+    float2 C = make_float2(0.f, 0.f);
+    if (batch < n_batches && batch * (G3_BATCH * 32u) + lane < p.n_tri) {
+        const uint32_t t0 = batch * (G3_BATCH * 32u) + lane;
+        A = __ldg(sc.a + t0); B = __ldg(sc.b + t0); C = __ldg(sc.c + t0);
+    }
+    for (; batch < n_batches; batch += n_warps) {
+        const uint32_t c_end = min(n_chunks, (batch + 1u) * G3_BATCH);
+        for (uint32_t c = batch * G3_BATCH; c < c_end; ++c) {
+            const uint32_t t = c * 32u + lane;
+            const float v0 = A.x, v1 = A.y, v2 = A.z, v3 = A.w, v4 = B.x, v5 = B.y, v6 = B.z, v7 = B.w, v8 = C.x;
+            {   // prefetch the next chunk of this warp (next in the batch, or first of its next batch)
+                const uint32_t cn = (c + 1u < c_end) ? c + 1u : (batch + n_warps) * G3_BATCH;
+                const uint32_t tn = cn * 32u + lane;
+                if (cn < n_chunks && tn < p.n_tri) { A = __ldg(sc.a + tn); B = __ldg(sc.b + tn); C = __ldg(sc.c + tn); }
+            }
+            // ---- phase A: x'/y' transform, bounds (Triangle::mul, aabb, rasterizer.rs:58-66) --
+            const float y1 = xform_row(p.m + 4, v0, v1, v2), x1 = xform_row(p.m + 0, v0, v1, v2);
+            const float y2 = xform_row(p.m + 4, v3, v4, v5), x2 = xform_row(p.m + 0, v3, v4, v5);
+            const float y3 = xform_row(p.m + 4, v6, v7, v8), x3 = xform_row(p.m + 0, v6, v7, v8);
+            const float mn1 = fminf(y1, fminf(y2, y3)), mx1 = fmaxf(y1, fmaxf(y2, y3));
+            const float mn0 = fminf(x1, fminf(x2, x3)), mx0 = fmaxf(x1, fmaxf(x2, x3));
+            const uint32_t miny = __float2uint_rz(ceilf(fmaxf(mn1, 1.0f)));
+            const uint32_t maxy = __float2uint_rz(ceilf(fminf(mx1, p.hm1)));
+            const uint32_t minx = __float2uint_rz(ceilf(fmaxf(mn0, 1.0f)));
+            const uint32_t maxx = __float2uint_rz(ceilf(fminf(mul(mx0, 2.0f), p.wm1)));
+            const bool has_rows = t < p.n_tri && miny < maxy && miny < p.row1 && maxy + 1u > p.krow0;
+
+            // ---- row stamps (rasterizer.rs:89-91) + row hull of the chunk ---------------------
+            // Stamps go to a per-block bitmap in shared memory (flushed once at the end): every
+            // warp in flight stamps the same few rows, and same-address traffic serialises in L2.
+            if (do_stamps) {
+                const uint32_t sy0 = max(miny, p.row0), sy1 = min(maxy, p.row1);
+                const bool st = has_rows && sy0 < sy1;
+                const uint32_t ymin = __reduce_min_sync(0xFFFFFFFFu, st ? sy0 : 0xFFFFFFFFu);
+                const uint32_t hmin = __reduce_min_sync(0xFFFFFFFFu, has_rows ? miny : 0xFFFFFFFFu);
+                const uint32_t hmax = __reduce_max_sync(0xFFFFFFFFu, has_rows ? maxy : 0u);
+                if (lane == 0) chunk_hull[c] = hmin == 0xFFFFFFFFu ? 0u : (hmin | (hmax << 16));
+                if (ymin != 0xFFFFFFFFu) {
+                    const uint32_t wmin = ymin >> 5;
+                    const uint32_t lo = sy0 - (wmin << 5), n = sy1 - sy0;   // meaningful when st
+                    const bool fits = st && lo + n <= 64u;                  // inside the 2-word window
+                    unsigned long long m64 = 0ull;
+                    if (fits) m64 = (n >= 64u ? ~0ull : ((1ull << n) - 1ull)) << lo;
+                    const uint32_t need0 = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)m64);
+                    const uint32_t need1 = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(m64 >> 32));
+                    if (lane < 2u) {
+                        const uint32_t mine = lane == 0 ? need0 : need1;
+                        if (mine) atomicOr(s_rowbits + wmin + lane, mine);
+                    }
+                    if (st && !fits)   // tall or far-away triangle: word by word
+                        for (uint32_t w = sy0 >> 5; w <= (sy1 - 1u) >> 5; ++w)
+                            atomicOr(s_rowbits + w, row_mask_in_word(sy0, sy1, w));
+                }
+            }
+
+            // ---- classification ---------------------------------------------------------------
+            const bool live = has_rows && minx < maxx;
+            bool regular = true;
+            if (CHECK_REGULAR)   // x/y only: z never enters coverage, it is evaluated exactly per fragment
+                regular = in_limit(x1) && in_limit(y1) && in_limit(x2) && in_limit(y2) && in_limit(x3) && in_limit(y3);
+            const float dx0 = sub(x3, x2), dy0 = sub(y3, y2);
+            const float dx1 = sub(x1, x3), dy1 = sub(y1, y3);
+            const float dx2 = sub(x2, x1), dy2 = sub(y2, y1);
+            const bool cand = live && regular && !backface_proven(p, dx1, dy1, dx2, dy2, mn0, mx0, mn1, mx1);
+            const uint32_t rows = maxy - miny, span = maxx - minx;
+            uint32_t tw;
+            {
+                const uint32_t f = __float2uint_rz(floorf(mx0));
+                const uint32_t te = f >= maxx ? maxx : f + 1u;
+                tw = te > minx ? te - minx : 0u;
+            }
+            const bool foot = cand && rows <= 2u && tw <= 2u;
+            uint32_t walk_items = 0;
+            if (cand && !foot) walk_items = (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw);
+
+            // ---- phase B: 2 x 3 footprint in registers ----------------------------------------
+            uint32_t mask = 0;
+            if (__any_sync(0xFFFFFFFFu, foot)) {
+                const bool nd0 = !(dy0 < 0.0f), nd1 = !(dy1 < 0.0f), nd2 = !(dy2 < 0.0f);
+                float cr[2][3], gc[3][3];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const float py = (float)(miny + r);
+                    cr[r][0] = mul(dx0, sub(py, y2));
+                    cr[r][1] = mul(dx1, sub(py, y3));
+                    cr[r][2] = mul(dx2, sub(py, y1));
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float px = (float)(minx + k);
+                    gc[k][0] = mul(dy0, sub(px, x2));
+                    gc[k][1] = mul(dy1, sub(px, x3));
+                    gc[k][2] = mul(dy2, sub(px, x1));
+                }
+                bool open = false;   // some active row is not provably finished after column 2
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const bool n0 = sub(cr[r][0], gc[k][0]) < 0.0f;
+                        const bool n1 = sub(cr[r][1], gc[k][1]) < 0.0f;
+                        const bool n2 = sub(cr[r][2], gc[k][2]) < 0.0f;
+                        // regular triangle: no NaN, so "all >= 0" == "none < 0"
+                        if (!(n0 || n1 || n2) && (uint32_t)r < rows && (uint32_t)k < span) mask |= 1u << (r * 3 + k);
+                        if (k == 2 && (uint32_t)r < rows && span > 3u && !((n0 && nd0) || (n1 && nd1) || (n2 && nd2)))
+                            open = true;
+                    }
+                }
+                if (!foot) mask = 0;
+                else if (open) {   // sliver: hand the whole triangle to k_walk (exact, any width)
+                    mask = 0;
+                    walk_items = (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw);
+                }
+            }
+
+            // ---- phase C: queue covering triangles + one entry per fragment -------------------
+            const unsigned cov = __ballot_sync(0xFFFFFFFFu, mask != 0u);
+            if (cov) {
+                const uint32_t slot = n_tq + __popc(cov & ((1u << lane) - 1u));
+                if (mask) {
+                    wq.raw[0][slot] = v0; wq.raw[1][slot] = v1; wq.raw[2][slot] = v2;
+                    wq.raw[3][slot] = v3; wq.raw[4][slot] = v4; wq.raw[5][slot] = v5;
+                    wq.raw[6][slot] = v6; wq.raw[7][slot] = v7; wq.raw[8][slot] = v8;
+                    wq.tri[slot] = t;
+                    wq.xy[slot] = minx | (miny << 16);
+                }
+#pragma unroll
+                for (uint32_t b = 0; b < 6u; ++b) {
+                    const unsigned bb = __ballot_sync(0xFFFFFFFFu, (mask >> b) & 1u);
+                    if ((mask >> b) & 1u) wq.frag[n_fq + __popc(bb & ((1u << lane) - 1u))] = (uint16_t)(slot | (b << 8));
+                    n_fq += __popc(bb);
+                }
+                n_tq += __popc(cov);
+                if (n_fq >= G3_FLUSH || n_tq > G3_TRI_CAP - 32u) {
+                    __syncwarp();
+                    g3_emit_all(p, wq, n_fq, lane, keys, nfrag_count);
+                    __syncwarp();
+                    n_fq = 0; n_tq = 0;
+                }
+            }
+
+            // ---- rare: queue pushes for k_walk / k_irregular (one atomic per warp) ------------
+            const unsigned need = __ballot_sync(0xFFFFFFFFu, walk_items > 0);
+            if (need) {
+                uint32_t wi = walk_items;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                    if ((int)lane >= d) wi += n;
+                }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, wi, 31);
+                unsigned long long old = 0;
+                if (lane == 0)
+                    old = atomicAdd(&q.aux->walk_counter, ((unsigned long long)__popc(need) << ITEM_BITS) | total);
+                old = __shfl_sync(0xFFFFFFFFu, old, 0);
+                if (walk_items > 0) {
+                    const uint32_t slot = (uint32_t)(old >> ITEM_BITS) + __popc(need & ((1u << lane) - 1u));
+                    q.walk_tri[slot] = t;
+                    q.walk_base[slot] = (old & ITEM_MASK) + (wi - walk_items);
+                }
+            }
+            if (CHECK_REGULAR) {
+                const unsigned irr = __ballot_sync(0xFFFFFFFFu, live && !regular);
+                if (irr) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&q.aux->irr_count, (uint32_t)__popc(irr));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (live && !regular) q.irr_tri[base + __popc(irr & ((1u << lane) - 1u))] = t;
+                }
+            }
+        }
+    }
+    if (n_fq) {
+        __syncwarp();
+        g3_emit_all(p, wq, n_fq, lane, keys, nfrag_count);
+    }
+    if (do_stamps) {   // publish this block's stamped rows
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n_row_words - 1u; i += blockDim.x) {
+            const uint32_t m = s_rowbits[i];
+            if (m && (__ldcg(q.rowbits + i) & m) != m) atomicOr(q.rowbits + i, m);
+        }
+    }
+    if (p.count_frags) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nfrag_count += __shfl_xor_sync(0xFFFFFFFFu, nfrag_count, d);
+        if (lane == 0 && nfrag_count) atomicAdd(&q.aux->frag_counter, (unsigned long long)nfrag_count);
+    }
+}
+
 // One warp per row-band item.  Lanes take 32 consecutive candidates of a row;
 // a row ends when any lane sees a closing edge fail (everything right of that
 // lane fails as well) or at the reference's maxx.
@@ -343,23 +650,39 @@ __global__ void __launch_bounds__(256) k_clear_keys_odd(unsigned long long* __re
     if (i < n) keys[i] = KEY_EMPTY;
 }
 
-// For every queued row: does a triangle with index >= the fragment's triangle
-// stamp that row?  Only the y-range of each triangle is needed.
+// For every queued row: does a triangle with index >= the fragment's triangle stamp
+// that row?  One warp per tile of 256 triangles; the tile's row hull (written by
+// k_geom2) rejects almost every tile without touching its triangles.
 __global__ void __launch_bounds__(256) k_stampfix_scan(const __grid_constant__ FrameParams p, const Scene sc,
-                                                       const Queues q)
+                                                       const Queues q, const uint32_t* __restrict__ tile_hull,
+                                                       const uint32_t use_hull, const uint32_t hull_tile)
 {
     const uint32_t n_fix = q.aux->fix_count;
     if (n_fix == 0) return;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < p.n_tri; t += gridDim.x * blockDim.x) {
-        float v[9];
-        uint32_t rgb;
-        load_tri(sc, t, v, rgb);
-        Setup s;
-        setup_tri(p, v, s);
-        if (s.miny >= s.maxy) continue;
-        for (uint32_t i = 0; i < n_fix; ++i) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n_tiles = (p.n_tri + hull_tile - 1u) / hull_tile;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles; tile += n_warps) {
+        const uint32_t hull = use_hull ? tile_hull[tile] : 0xFFFF0000u;
+        const uint32_t hmin = hull & 0xFFFFu, hmax = hull >> 16;
+        const uint32_t t_last = min(p.n_tri, (tile + 1u) * hull_tile) - 1u;
+        bool cand = false;
+        for (uint32_t i = lane; i < n_fix; i += 32u) {
             const uint32_t row = q.fix_rows[i];
-            if (t >= q.fix_tri[i] && row >= s.miny && row < s.maxy) q.fix_newline[i] = 1u;
+            cand = cand || (t_last >= q.fix_tri[i] && row >= hmin && row < hmax);
+        }
+        if (!__any_sync(0xFFFFFFFFu, cand)) continue;
+        for (uint32_t t = tile * hull_tile + lane; t <= t_last; t += 32u) {
+            float v[9];
+            uint32_t rgb;
+            load_tri(sc, t, v, rgb);
+            Setup s;
+            setup_tri(p, v, s);
+            if (s.miny >= s.maxy) continue;
+            for (uint32_t i = 0; i < n_fix; ++i) {
+                const uint32_t row = q.fix_rows[i];
+                if (t >= q.fix_tri[i] && row >= s.miny && row < s.maxy) q.fix_newline[i] = 1u;
+            }
         }
     }
 }

@@ -36,6 +36,7 @@ struct FrameParams {
     uint32_t n_tri;
     uint32_t image;    // Context.image
     uint32_t count_frags;
+    uint32_t debug;    // profiling experiments only (SLOTH_DEBUG): 1 = skip key atomics, 2 = skip row stamps
     char glyph[12];    // 10 glyphs (+pad)
 };
 
@@ -200,7 +201,7 @@ SLOTH_DEV void emit_fragment(const FrameParams& p, const Setup& s, const Shade& 
     const unsigned long long key =
         ((unsigned long long)ord << 32) | (unsigned long long)((tri << 5) | (direct << 4) | g);
     const uint32_t L = y * p.KW + kx - p.krow0 * p.KW;
-    atomicMin(keys + L, key);
+    if (!(p.debug & 1u)) atomicMin(keys + L, key);
 }
 
 // Number of rows one row-band work item of the walk kernel covers.
