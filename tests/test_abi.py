@@ -1,0 +1,82 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads and exports every
+symbol include/sloth_b200.h declares; the host helpers agree with the oracle; and without
+a GPU the product fails loudly instead of falling back to anything."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+import rust_sloth_b200 as rs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "sloth_b200.h")).read()
+    return sorted(set(re.findall(r"SLOTH_API\s+[^;(]*?\b(sloth_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = rs.load_library()
+    names = header_symbols()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(L, n), f"{n} is declared in include/sloth_b200.h but not exported"
+    assert sorted(rs.ABI_SYMBOLS) == names
+    out = subprocess.run(["nm", "-D", "--defined-only", rs.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (\w+)", out))
+    assert set(names) <= exported
+    # nothing but the ABI leaks out of the library
+    assert all(e.startswith("sloth_") for e in exported), exported - set(names)
+
+
+def test_library_is_built_for_sm_100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", rs.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(rs.SlothError) as e:
+        rs.Context.blank(True)
+    assert e.value.code == rs.SLOTH_E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "rust-sloth_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in text.lower() or f == "__init__.py" and "import oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_host_helpers_match_the_oracle():
+    for (r, p, y) in [(0.0, np.pi, 0.0), (0.3, 3.3, -0.7), (1e-3, 9.4, 2.0), (-2.0, 0.1, 7.0)]:
+        assert np.array_equal(rs.rotation_from_euler(r, p, y), oracle.rotation(r, p, y))
+    for (W, H, s) in [(80, 40, 7.534395), (1920, 1080, 0.958196), (3840, 2160, 1.0), (101, 57, 1.367188), (65536, 65536, 1.0), (7, 200, 0.0)]:
+        a, b = rs.utransform(W, H, s), oracle.utransform(W, H, s)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for (y0, n) in [(0.0, 360), (0.0, 64), (0.0, 1), (5.0, 100), (-1.0, 7)]:
+        assert np.array_equal(rs.turntable_pitches(y0, n), oracle.turntable(y0, n))
+
+
+def test_default_shader_table():
+    assert "".join(rs.default_shader(s) for s in [0.0, 0.2, 0.25, 0.3, 0.45, 0.55, 0.65, 0.75, 0.85, 0.95, 1.0]) == "..::=+*#%@@"
+    assert rs.default_shader(1.0001) == " " and rs.default_shader(float("nan")) == " " and rs.default_shader(-5) == "."
+
+
+def test_flush_formats():
+    cells = np.array([ord("@") | 1 << 8 | 2 << 16 | 3 << 24, ord("\n"), ord(" ")], np.uint32)
+    assert rs.flush_bytes(cells, False, False, True) == b"@\n \n"
+    assert rs.flush_bytes(cells, True, True, True) == (b'<span style="color:rgb(1,2,3)">@<span style="color:rgb(0,0,0)">\n'
+                                                      b'<span style="color:rgb(0,0,0)"> ')
+    ansi = rs.flush_bytes(cells[:1], True, False, False)
+    assert ansi == b"\x1b[1;1H\x1b[38;2;1;2;3m\x1b[48;2;25;25;25m@\x1b[0m"
