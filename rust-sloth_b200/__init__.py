@@ -435,8 +435,8 @@ def flush_bytes(cells: np.ndarray, color: bool, webify: bool, image: bool) -> by
     * no colour: every glyph, then '\\n' (println!)
     * colour + webify: ``<span style="color:rgb(r,g,b)">c`` per cell, never closed
     * colour: crossterm 0.18 PrintStyledContent with fg = cell colour, bg = rgb(25,25,25):
-      ``ESC[38;2;r;g;bm ESC[48;2;25;25;25m c ESC[0m`` (restated from crossterm's
-      documented behaviour: foreground first, then background, reset after; unpinned).
+      ``ESC[48;2;25;25;25m ESC[38;2;r;g;bm c ESC[0m`` (restated from crossterm 0.18's
+      ``Display for StyledContent``: background, foreground, content, ResetColor; unpinned).
     Interactive mode additionally starts with ``ESC[1;1H`` (cursor::MoveTo(0,0)).
     """
     cells = np.asarray(cells, np.uint32)
@@ -454,7 +454,7 @@ def flush_bytes(cells: np.ndarray, color: bool, webify: bool, image: bool) -> by
             out.append(glyph[i])
     else:
         for i in range(cells.size):
-            out += b"\x1b[38;2;%d;%d;%dm\x1b[48;2;25;25;25m" % (r[i], g[i], b[i])
+            out += b"\x1b[48;2;25;25;25m\x1b[38;2;%d;%d;%dm" % (r[i], g[i], b[i])
             out.append(glyph[i])
             out += b"\x1b[0m"
     return bytes(out)

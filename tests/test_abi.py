@@ -79,4 +79,4 @@ def test_flush_formats():
     assert rs.flush_bytes(cells, True, True, True) == (b'<span style="color:rgb(1,2,3)">@<span style="color:rgb(0,0,0)">\n'
                                                       b'<span style="color:rgb(0,0,0)"> ')
     ansi = rs.flush_bytes(cells[:1], True, False, False)
-    assert ansi == b"\x1b[1;1H\x1b[38;2;1;2;3m\x1b[48;2;25;25;25m@\x1b[0m"
+    assert ansi == b"\x1b[1;1H\x1b[48;2;25;25;25m\x1b[38;2;1;2;3m@\x1b[0m"

@@ -1,6 +1,7 @@
 """GPU parity: the CUDA path through the C ABI vs the CPU oracle, bit for bit
 (cells: glyph + colour of every terminal cell; z-buffer: every depth winner)."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -172,3 +173,31 @@ def test_reference_style_host_api():
     gold = [c for c in S.golden()["cases"] if c["scene"] == "pikachu" and c["W"] == 80][0]
     assert text == gold["text"] + "\n"
     context.close()
+
+
+def _write_obj(path, xyz):
+    with open(path, "w") as f:
+        for v in xyz.reshape(-1, 3):
+            f.write("v %s %s %s\n" % tuple(repr(float(np.float32(c))) for c in v))
+        for t in range(xyz.shape[0]):
+            f.write("f %d %d %d\n" % (3 * t + 1, 3 * t + 2, 3 * t + 3))
+
+
+def test_cli_drop_in_image_and_webify(tmp_path):
+    """The C++ `sloth` binary: `image -w -h` text and the `-j` JS-frame export, byte for byte."""
+    import subprocess
+    from rust_sloth_b200 import turntable as tt
+    exe = os.path.join(os.path.dirname(rs.LIB_PATH), "bin", "sloth")
+    xyz, rgb, s0 = S.soup("pikachu")
+    obj = str(tmp_path / "pikachu.obj")
+    _write_obj(obj, xyz)
+    white = np.ones_like(rgb)                       # no mtllib -> colour (1,1,1), geometry.rs:91
+    out = subprocess.run([exe, obj, "-b", "image", "-w", "80", "-h", "40"], capture_output=True, check=True).stdout
+    gold = [c for c in S.golden()["cases"] if c["scene"] == "pikachu" and c["W"] == 80][0]
+    assert out.decode("latin-1") == gold["text"] + "\n"
+    out = subprocess.run([exe, obj, "image", "-w", "64", "-h", "30", "-j", "5", "-x", "0.25"], capture_output=True, check=True).stdout
+    frames = [oracle.render(xyz, white, s0, 64, 30, oracle.rotation(0.25, p, 0.0), mode=0)[0] for p in oracle.turntable(0.0, 5)]
+    assert out == tt.webify_stream(frames)
+    out = subprocess.run([exe, obj, "image", "-w", "31"], capture_output=True, check=True).stdout   # -h defaults to -w, colour on
+    cells = oracle.render(xyz, white, s0, 31, 31, oracle.rotation(0.0, S.PI, 0.0), mode=0)[0]
+    assert out == rs.flush_bytes(cells, True, False, True)
