@@ -223,8 +223,10 @@ int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z
             bool bounded = c->scene_clean;
             for (int i = 0; i < 8; ++i) bounded = bounded && std::fabs(p.m[i]) <= 131072.0f;
             const size_t dyn = (((size_t)c->H + 31) / 32 + 1) * sizeof(uint32_t);   // per-block row-stamp bitmap
-            if (bounded) k_geom3<false><<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->keys, q, c->tile_hull);
-            else k_geom3<true><<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->keys, q, c->tile_hull);
+            const bool band_mode = c->row1 != 0;
+            auto kern = bounded ? (band_mode ? k_geom3<false, true> : k_geom3<false, false>)
+                                : (band_mode ? k_geom3<true, true> : k_geom3<true, false>);
+            kern<<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->keys, q, c->tile_hull);
         }
         if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
         k_walk<<<c->sm_count * 8, 128, 0, st>>>(p, sc, c->keys, q);
@@ -259,7 +261,7 @@ int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z
         c->launches += 2;
     }
     if (c->image && c->n_tri) {
-        k_stampfix_scan<<<c->sm_count * 4, 256, 0, st>>>(p, sc, q, c->tile_hull, c->geom_variant == 1 ? 0u : 1u, c->geom_variant == 1 ? GEOM_TILE : 32u);
+        k_stampfix_scan<<<c->sm_count * 4, 256, 0, st>>>(p, sc, q, c->tile_hull, c->geom_variant == 1 ? 0u : 1u, c->geom_variant == 1 ? GEOM_TILE : G3_BATCH * 32u);
         k_stampfix_apply<<<1, 256, 0, st>>>(p, q, d_out);
         c->launches += 2;
     }

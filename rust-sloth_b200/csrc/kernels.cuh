@@ -178,22 +178,20 @@ static constexpr uint32_t GEOM_TILE = 256;   // triangles per block of the first
 //      cost 2x3 row terms + 3x3 column terms + 18 subtractions.  Nothing can be
 //      covered right of a column where a closing edge already fails (row_closed);
 //      if that cannot be shown inside the footprint the triangle goes to k_walk.
-//   C  covering triangles are parked in a per-warp shared-memory queue, one entry
-//      per fragment; when >= 64 fragments are queued they are emitted with all
-//      lanes busy: re-transform (now with z'), normal, depth, glyph, 64-bit
-//      atomicMin into the key plane.
+//   C  covering triangles are parked in a per-warp shared-memory ring; whenever 32
+//      are queued they are emitted with all lanes busy: lane = triangle, full
+//      re-transform (now with z'), normal and 1/area once, then per footprint bit
+//      one edge evaluation, depth, glyph and a 64-bit atomicMin into the key plane.
 // ---------------------------------------------------------------------------------
 static constexpr uint32_t G3_WARPS = 8;          // warps per block
 static constexpr uint32_t G3_BATCH = 16;         // consecutive chunks per warp turn
-static constexpr uint32_t G3_TRI_CAP = 96;       // queued covering triangles per warp
-static constexpr uint32_t G3_FRAG_CAP = 256;     // queued fragments per warp (64 + 32*6)
-static constexpr uint32_t G3_FLUSH = 64;
+static constexpr uint32_t G3_RING = 64;          // per-warp ring of covering triangles (power of two)
 
 struct G3Queue {
-    float raw[9][G3_TRI_CAP];     // object-space vertices
-    uint32_t tri[G3_TRI_CAP];
-    uint32_t xy[G3_TRI_CAP];      // minx | miny << 16
-    uint16_t frag[G3_FRAG_CAP];   // queue slot | footprint bit << 8   (bit = row*3 + col)
+    float raw[9][G3_RING];        // object-space vertices
+    uint32_t tri[G3_RING];
+    uint32_t xy[G3_RING];         // minx | miny << 16
+    uint32_t mask[G3_RING];       // footprint bits: bit = row*3 + col
 };
 
 // No candidate of the scan domain can pass all three edge tests when the computed
@@ -216,41 +214,49 @@ SLOTH_DEV bool backface_proven(const FrameParams& p, float dx1, float dy1, float
     return T > 1e-30f && area < -T;
 }
 
-SLOTH_DEV void g3_emit_all(const FrameParams& p, const G3Queue& wq, uint32_t n_fq, uint32_t lane,
-                           unsigned long long* __restrict__ keys, uint32_t& nfrag_count)
+// Emit the fragments of `count` queued triangles starting at ring position `head`:
+// lane = triangle; the per-triangle work (full transform now including z', normal,
+// 1/area) is done once, then each footprint bit costs one edge evaluation + depth +
+// glyph + atomicMin.
+SLOTH_DEV void g3_emit(const FrameParams& p, const G3Queue& wq, uint32_t head, uint32_t count, uint32_t lane,
+                       unsigned long long* __restrict__ keys, uint32_t& nfrag_count)
 {
-    for (uint32_t f = lane; f < n_fq; f += 32u) {
-        const uint32_t e = wq.frag[f], slot = e & 255u, bit = e >> 8;
-        float v[9];
+    if (lane >= count) return;
+    const uint32_t slot = (head + lane) & (G3_RING - 1u);
+    float v[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) v[k] = wq.raw[k][slot];
-        // same operations on the same inputs as phase A: bit-identical x', y'
-        Setup s;
-        s.x1 = xform_row(p.m + 0, v[0], v[1], v[2]); s.y1 = xform_row(p.m + 4, v[0], v[1], v[2]);
-        s.z1 = xform_row(p.m + 8, v[0], v[1], v[2]);
-        s.x2 = xform_row(p.m + 0, v[3], v[4], v[5]); s.y2 = xform_row(p.m + 4, v[3], v[4], v[5]);
-        s.z2 = xform_row(p.m + 8, v[3], v[4], v[5]);
-        s.x3 = xform_row(p.m + 0, v[6], v[7], v[8]); s.y3 = xform_row(p.m + 4, v[6], v[7], v[8]);
-        s.z3 = xform_row(p.m + 8, v[6], v[7], v[8]);
-        s.dx0 = sub(s.x3, s.x2); s.dy0 = sub(s.y3, s.y2);
-        s.dx1 = sub(s.x1, s.x3); s.dy1 = sub(s.y1, s.y3);
-        s.dx2 = sub(s.x2, s.x1); s.dy2 = sub(s.y2, s.y1);
-        const uint32_t xy = wq.xy[slot];
+    for (int k = 0; k < 9; ++k) v[k] = wq.raw[k][slot];
+    // same operations on the same inputs as phase A: bit-identical x', y'
+    Setup s;
+    s.x1 = xform_row(p.m + 0, v[0], v[1], v[2]); s.y1 = xform_row(p.m + 4, v[0], v[1], v[2]);
+    s.z1 = xform_row(p.m + 8, v[0], v[1], v[2]);
+    s.x2 = xform_row(p.m + 0, v[3], v[4], v[5]); s.y2 = xform_row(p.m + 4, v[3], v[4], v[5]);
+    s.z2 = xform_row(p.m + 8, v[3], v[4], v[5]);
+    s.x3 = xform_row(p.m + 0, v[6], v[7], v[8]); s.y3 = xform_row(p.m + 4, v[6], v[7], v[8]);
+    s.z3 = xform_row(p.m + 8, v[6], v[7], v[8]);
+    s.dx0 = sub(s.x3, s.x2); s.dy0 = sub(s.y3, s.y2);
+    s.dx1 = sub(s.x1, s.x3); s.dy1 = sub(s.y1, s.y3);
+    s.dx2 = sub(s.x2, s.x1); s.dy2 = sub(s.y2, s.y1);
+    Shade sh;
+    shade_setup(s, sh);
+    const uint32_t xy = wq.xy[slot], tri = wq.tri[slot];
+    uint32_t mask = wq.mask[slot];
+    while (mask) {
+        const uint32_t bit = __ffs(mask) - 1u;
+        mask &= mask - 1u;
         const uint32_t x = (xy & 0xFFFFu) + (bit >= 3u ? bit - 3u : bit), y = (xy >> 16) + (bit >= 3u ? 1u : 0u);
         const RowC rc = row_setup(s, y);
         float w0, w1, w2;
         edge_eval(s, rc, x, w0, w1, w2);
-        Shade sh;
-        shade_setup(s, sh);
-        emit_fragment(p, s, sh, wq.tri[slot], x, y, w0, w1, w2, keys);
+        emit_fragment(p, s, sh, tri, x, y, w0, w1, w2, keys);
         ++nfrag_count;
     }
 }
 
-template <bool CHECK_REGULAR>
+template <bool CHECK_REGULAR, bool BAND>
 __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constant__ FrameParams p, const Scene sc,
                                                             unsigned long long* __restrict__ keys, const Queues q,
-                                                            uint32_t* __restrict__ chunk_hull)
+                                                            uint32_t* __restrict__ batch_hull)
 {
     __shared__ G3Queue queues[G3_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
     const uint32_t n_chunks = (p.n_tri + 31u) >> 5;
     const uint32_t n_batches = (n_chunks + G3_BATCH - 1u) / G3_BATCH;
     const uint32_t n_warps = gridDim.x * G3_WARPS;
-    uint32_t n_tq = 0, n_fq = 0, nfrag_count = 0;
+    uint32_t q_head = 0, q_count = 0, nfrag_count = 0;   // warp-uniform ring state
     const bool do_stamps = p.image && !(p.debug & 2u);
     extern __shared__ uint32_t s_rowbits[];   // (H+31)/32 + 1 words: rows stamped by this block
     const uint32_t n_row_words = ((p.H + 31u) >> 5) + 1u;
@@ -276,6 +282,7 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
     }
     for (; batch < n_batches; batch += n_warps) {
         const uint32_t c_end = min(n_chunks, (batch + 1u) * G3_BATCH);
+        uint32_t hull_lo = 0xFFFFFFFFu, hull_hi = 0u;   // per-lane row hull of this batch (for k_stampfix_scan)
         for (uint32_t c = batch * G3_BATCH; c < c_end; ++c) {
             const uint32_t t = c * 32u + lane;
             const float v0 = A.x, v1 = A.y, v2 = A.z, v3 = A.w, v4 = B.x, v5 = B.y, v6 = B.z, v7 = B.w, v8 = C.x;
@@ -294,24 +301,24 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
             const uint32_t maxy = __float2uint_rz(ceilf(fminf(mx1, p.hm1)));
             const uint32_t minx = __float2uint_rz(ceilf(fmaxf(mn0, 1.0f)));
             const uint32_t maxx = __float2uint_rz(ceilf(fminf(mul(mx0, 2.0f), p.wm1)));
-            const bool has_rows = t < p.n_tri && miny < maxy && miny < p.row1 && maxy + 1u > p.krow0;
+            // whole-frame contexts own every row; band contexts skip triangles whose destination
+            // rows (y, or y+1 after a row wrap) miss the band
+            const bool has_rows = t < p.n_tri && miny < maxy && (!BAND || (miny < p.row1 && maxy + 1u > p.krow0));
 
-            // ---- row stamps (rasterizer.rs:89-91) + row hull of the chunk ---------------------
+            // ---- row stamps (rasterizer.rs:89-91) + row hull of the batch ---------------------
             // Stamps go to a per-block bitmap in shared memory (flushed once at the end): every
             // warp in flight stamps the same few rows, and same-address traffic serialises in L2.
             if (do_stamps) {
-                const uint32_t sy0 = max(miny, p.row0), sy1 = min(maxy, p.row1);
+                const uint32_t sy0 = BAND ? max(miny, p.row0) : miny, sy1 = BAND ? min(maxy, p.row1) : maxy;
                 const bool st = has_rows && sy0 < sy1;
+                if (has_rows) { hull_lo = min(hull_lo, miny); hull_hi = max(hull_hi, maxy); }   // reduced once per batch
                 const uint32_t ymin = __reduce_min_sync(0xFFFFFFFFu, st ? sy0 : 0xFFFFFFFFu);
-                const uint32_t hmin = __reduce_min_sync(0xFFFFFFFFu, has_rows ? miny : 0xFFFFFFFFu);
-                const uint32_t hmax = __reduce_max_sync(0xFFFFFFFFu, has_rows ? maxy : 0u);
-                if (lane == 0) chunk_hull[c] = hmin == 0xFFFFFFFFu ? 0u : (hmin | (hmax << 16));
                 if (ymin != 0xFFFFFFFFu) {
                     const uint32_t wmin = ymin >> 5;
                     const uint32_t lo = sy0 - (wmin << 5), n = sy1 - sy0;   // meaningful when st
-                    const bool fits = st && lo + n <= 64u;                  // inside the 2-word window
+                    const bool fits = st && n <= 32u && lo + n <= 64u;      // inside the 2-word window
                     unsigned long long m64 = 0ull;
-                    if (fits) m64 = (n >= 64u ? ~0ull : ((1ull << n) - 1ull)) << lo;
+                    if (fits) m64 = (unsigned long long)(0xFFFFFFFFu >> (32u - n)) << lo;
                     const uint32_t need0 = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)m64);
                     const uint32_t need1 = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(m64 >> 32));
                     if (lane < 2u) {
@@ -384,29 +391,25 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
                 }
             }
 
-            // ---- phase C: queue covering triangles + one entry per fragment -------------------
+            // ---- phase C: park covering triangles; emit 32 at a time --------------------------
             const unsigned cov = __ballot_sync(0xFFFFFFFFu, mask != 0u);
             if (cov) {
-                const uint32_t slot = n_tq + __popc(cov & ((1u << lane) - 1u));
                 if (mask) {
+                    const uint32_t slot = (q_head + q_count + __popc(cov & ((1u << lane) - 1u))) & (G3_RING - 1u);
                     wq.raw[0][slot] = v0; wq.raw[1][slot] = v1; wq.raw[2][slot] = v2;
                     wq.raw[3][slot] = v3; wq.raw[4][slot] = v4; wq.raw[5][slot] = v5;
                     wq.raw[6][slot] = v6; wq.raw[7][slot] = v7; wq.raw[8][slot] = v8;
                     wq.tri[slot] = t;
                     wq.xy[slot] = minx | (miny << 16);
+                    wq.mask[slot] = mask;
                 }
-#pragma unroll
-                for (uint32_t b = 0; b < 6u; ++b) {
-                    const unsigned bb = __ballot_sync(0xFFFFFFFFu, (mask >> b) & 1u);
-                    if ((mask >> b) & 1u) wq.frag[n_fq + __popc(bb & ((1u << lane) - 1u))] = (uint16_t)(slot | (b << 8));
-                    n_fq += __popc(bb);
-                }
-                n_tq += __popc(cov);
-                if (n_fq >= G3_FLUSH || n_tq > G3_TRI_CAP - 32u) {
+                q_count += __popc(cov);
+                if (q_count >= 32u) {
                     __syncwarp();
-                    g3_emit_all(p, wq, n_fq, lane, keys, nfrag_count);
+                    g3_emit(p, wq, q_head, 32u, lane, keys, nfrag_count);
                     __syncwarp();
-                    n_fq = 0; n_tq = 0;
+                    q_head = (q_head + 32u) & (G3_RING - 1u);
+                    q_count -= 32u;
                 }
             }
 
@@ -440,10 +443,15 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
                 }
             }
         }
+        if (do_stamps) {
+            const uint32_t hmin = __reduce_min_sync(0xFFFFFFFFu, hull_lo);
+            const uint32_t hmax = __reduce_max_sync(0xFFFFFFFFu, hull_hi);
+            if (lane == 0) batch_hull[batch] = hmin == 0xFFFFFFFFu ? 0u : (hmin | (hmax << 16));
+        }
     }
-    if (n_fq) {
+    if (q_count) {
         __syncwarp();
-        g3_emit_all(p, wq, n_fq, lane, keys, nfrag_count);
+        g3_emit(p, wq, q_head, q_count, lane, keys, nfrag_count);
     }
     if (do_stamps) {   // publish this block's stamped rows
         __syncthreads();
@@ -666,10 +674,10 @@ __global__ void __launch_bounds__(256) k_stampfix_scan(const __grid_constant__ F
         const uint32_t hull = use_hull ? tile_hull[tile] : 0xFFFF0000u;
         const uint32_t hmin = hull & 0xFFFFu, hmax = hull >> 16;
         const uint32_t t_last = min(p.n_tri, (tile + 1u) * hull_tile) - 1u;
-        bool cand = false;
+        bool cand = false;   // any still-undecided entry this tile could decide?
         for (uint32_t i = lane; i < n_fix; i += 32u) {
             const uint32_t row = q.fix_rows[i];
-            cand = cand || (t_last >= q.fix_tri[i] && row >= hmin && row < hmax);
+            cand = cand || (t_last >= q.fix_tri[i] && row >= hmin && row < hmax && __ldcg(q.fix_newline + i) == 0u);
         }
         if (!__any_sync(0xFFFFFFFFu, cand)) continue;
         for (uint32_t t = tile * hull_tile + lane; t <= t_last; t += 32u) {
