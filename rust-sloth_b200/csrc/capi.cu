@@ -96,6 +96,7 @@ struct sloth_ctx {
     uint32_t* walk_tri = nullptr;
     unsigned long long* walk_base = nullptr;
     uint32_t* irr_tri = nullptr;
+    uint32_t hull_tile = 32;         // triangles per row-hull record of the last frame
     uint32_t* tile_hull = nullptr;   // [ceil(n_tri/256)] row hull of each geometry tile
     int geom_variant = 3;            // SLOTH_GEOM=1 selects the first-generation kernel k_geom (A/B runs)
     uint32_t debug = 0;              // SLOTH_DEBUG bits, profiling experiments only
@@ -217,7 +218,12 @@ int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z
             k_geom<<<(c->n_tri + 255) / 256, 256, 0, st>>>(p, sc, c->keys, q);
         } else {
             const uint32_t n_chunks = (c->n_tri + 31) / 32;
-            const uint32_t n_batches = (n_chunks + G3_BATCH - 1) / G3_BATCH;
+            // consecutive chunks per warp turn: 16 for big scenes (coherent row stamps, fewer hull records),
+            // fewer when that would leave warps without work
+            const uint32_t warps_avail = (uint32_t)c->sm_count * 3u * G3_WARPS;
+            uint32_t batch_chunks = std::max<uint32_t>(1u, std::min<uint32_t>(G3_BATCH_MAX, n_chunks / (warps_avail * 4u)));
+            c->hull_tile = batch_chunks * 32u;
+            const uint32_t n_batches = (n_chunks + batch_chunks - 1) / batch_chunks;
             const uint32_t grid = std::min<uint32_t>((n_batches + G3_WARPS - 1) / G3_WARPS, (uint32_t)c->sm_count * 3u);
             // a clean scene under a bounded matrix cannot produce |x'|,|y'| > 2^40: skip the per-triangle test
             bool bounded = c->scene_clean;
@@ -226,7 +232,7 @@ int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z
             const bool band_mode = c->row1 != 0;
             auto kern = bounded ? (band_mode ? k_geom3<false, true> : k_geom3<false, false>)
                                 : (band_mode ? k_geom3<true, true> : k_geom3<true, false>);
-            kern<<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->keys, q, c->tile_hull);
+            kern<<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->keys, q, c->tile_hull, batch_chunks);
         }
         if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
         k_walk<<<c->sm_count * 8, 128, 0, st>>>(p, sc, c->keys, q);
@@ -261,7 +267,7 @@ int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z
         c->launches += 2;
     }
     if (c->image && c->n_tri) {
-        k_stampfix_scan<<<c->sm_count * 4, 256, 0, st>>>(p, sc, q, c->tile_hull, c->geom_variant == 1 ? 0u : 1u, c->geom_variant == 1 ? GEOM_TILE : G3_BATCH * 32u);
+        k_stampfix_scan<<<c->sm_count * 4, 256, 0, st>>>(p, sc, q, c->tile_hull, c->geom_variant == 1 ? 0u : 1u, c->geom_variant == 1 ? GEOM_TILE : c->hull_tile);
         k_stampfix_apply<<<1, 256, 0, st>>>(p, q, d_out);
         c->launches += 2;
     }

@@ -184,14 +184,15 @@ static constexpr uint32_t GEOM_TILE = 256;   // triangles per block of the first
 //      one edge evaluation, depth, glyph and a 64-bit atomicMin into the key plane.
 // ---------------------------------------------------------------------------------
 static constexpr uint32_t G3_WARPS = 8;          // warps per block
-static constexpr uint32_t G3_BATCH = 16;         // consecutive chunks per warp turn
+static constexpr uint32_t G3_BATCH_MAX = 16;     // consecutive chunks per warp turn (fewer for small scenes)
 static constexpr uint32_t G3_RING = 64;          // per-warp ring of covering triangles (power of two)
 
 struct G3Queue {
     float raw[9][G3_RING];        // object-space vertices
     uint32_t tri[G3_RING];
     uint32_t xy[G3_RING];         // minx | miny << 16
-    uint32_t mask[G3_RING];       // footprint bits: bit = row*3 + col
+    uint32_t mask_lo[G3_RING];    // footprint bits: bit = row*3 + col (2x3 tier) or row*8 + col (8x8 tier,
+    uint32_t mask_hi[G3_RING];    // flagged by bit 31 of tri[])
 };
 
 // No candidate of the scan domain can pass all three edge tests when the computed
@@ -239,12 +240,16 @@ SLOTH_DEV void g3_emit(const FrameParams& p, const G3Queue& wq, uint32_t head, u
     s.dx2 = sub(s.x2, s.x1); s.dy2 = sub(s.y2, s.y1);
     Shade sh;
     shade_setup(s, sh);
-    const uint32_t xy = wq.xy[slot], tri = wq.tri[slot];
-    uint32_t mask = wq.mask[slot];
+    const uint32_t xy = wq.xy[slot], tri_word = wq.tri[slot];
+    const uint32_t tri = tri_word & 0x7FFFFFFFu;
+    const bool wide = (tri_word >> 31) != 0u;   // 8x8 tier: bit = row*8 + col; else bit = row*3 + col
+    unsigned long long mask = ((unsigned long long)wq.mask_hi[slot] << 32) | wq.mask_lo[slot];
     while (mask) {
-        const uint32_t bit = __ffs(mask) - 1u;
-        mask &= mask - 1u;
-        const uint32_t x = (xy & 0xFFFFu) + (bit >= 3u ? bit - 3u : bit), y = (xy >> 16) + (bit >= 3u ? 1u : 0u);
+        const uint32_t bit = __ffsll((long long)mask) - 1u;
+        mask &= mask - 1ull;
+        const uint32_t r = wide ? (bit >> 3) : (bit >= 3u ? 1u : 0u);
+        const uint32_t k = wide ? (bit & 7u) : (bit >= 3u ? bit - 3u : bit);
+        const uint32_t x = (xy & 0xFFFFu) + k, y = (xy >> 16) + r;
         const RowC rc = row_setup(s, y);
         float w0, w1, w2;
         edge_eval(s, rc, x, w0, w1, w2);
@@ -256,13 +261,13 @@ SLOTH_DEV void g3_emit(const FrameParams& p, const G3Queue& wq, uint32_t head, u
 template <bool CHECK_REGULAR, bool BAND>
 __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constant__ FrameParams p, const Scene sc,
                                                             unsigned long long* __restrict__ keys, const Queues q,
-                                                            uint32_t* __restrict__ batch_hull)
+                                                            uint32_t* __restrict__ batch_hull, const uint32_t batch_chunks)
 {
     __shared__ G3Queue queues[G3_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     G3Queue& wq = queues[warp];
     const uint32_t n_chunks = (p.n_tri + 31u) >> 5;
-    const uint32_t n_batches = (n_chunks + G3_BATCH - 1u) / G3_BATCH;
+    const uint32_t n_batches = (n_chunks + batch_chunks - 1u) / batch_chunks;
     const uint32_t n_warps = gridDim.x * G3_WARPS;
     uint32_t q_head = 0, q_count = 0, nfrag_count = 0;   // warp-uniform ring state
     const bool do_stamps = p.image && !(p.debug & 2u);
@@ -276,18 +281,18 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
     uint32_t batch = blockIdx.x * G3_WARPS + warp;
     float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
     float2 C = make_float2(0.f, 0.f);
-    if (batch < n_batches && batch * (G3_BATCH * 32u) + lane < p.n_tri) {
-        const uint32_t t0 = batch * (G3_BATCH * 32u) + lane;
+    if (batch < n_batches && batch * (batch_chunks * 32u) + lane < p.n_tri) {
+        const uint32_t t0 = batch * (batch_chunks * 32u) + lane;
         A = __ldg(sc.a + t0); B = __ldg(sc.b + t0); C = __ldg(sc.c + t0);
     }
     for (; batch < n_batches; batch += n_warps) {
-        const uint32_t c_end = min(n_chunks, (batch + 1u) * G3_BATCH);
+        const uint32_t c_end = min(n_chunks, (batch + 1u) * batch_chunks);
         uint32_t hull_lo = 0xFFFFFFFFu, hull_hi = 0u;   // per-lane row hull of this batch (for k_stampfix_scan)
-        for (uint32_t c = batch * G3_BATCH; c < c_end; ++c) {
+        for (uint32_t c = batch * batch_chunks; c < c_end; ++c) {
             const uint32_t t = c * 32u + lane;
             const float v0 = A.x, v1 = A.y, v2 = A.z, v3 = A.w, v4 = B.x, v5 = B.y, v6 = B.z, v7 = B.w, v8 = C.x;
             {   // prefetch the next chunk of this warp (next in the batch, or first of its next batch)
-                const uint32_t cn = (c + 1u < c_end) ? c + 1u : (batch + n_warps) * G3_BATCH;
+                const uint32_t cn = (c + 1u < c_end) ? c + 1u : (batch + n_warps) * batch_chunks;
                 const uint32_t tn = cn * 32u + lane;
                 if (cn < n_chunks && tn < p.n_tri) { A = __ldg(sc.a + tn); B = __ldg(sc.b + tn); C = __ldg(sc.c + tn); }
             }
@@ -347,9 +352,10 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
                 const uint32_t te = f >= maxx ? maxx : f + 1u;
                 tw = te > minx ? te - minx : 0u;
             }
-            const bool foot = cand && rows <= 2u && tw <= 2u;
-            uint32_t walk_items = 0;
-            if (cand && !foot) walk_items = (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw);
+            const bool foot = cand && rows <= 2u && tw <= 2u;                  // tier 1: 2 x 3 footprint, lockstep
+            const bool mid = cand && !foot && rows <= 8u && tw <= 6u;           // tier 2: up to 8 x 8, per-lane loop
+            uint32_t walk_items = 0;                                            // tier 3: k_walk
+            if (cand && !foot && !mid) walk_items = (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw);
 
             // ---- phase B: 2 x 3 footprint in registers ----------------------------------------
             uint32_t mask = 0;
@@ -391,17 +397,43 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
                 }
             }
 
+            // ---- tier 2: triangles up to 8 rows x (6 + closing) columns, one lane each ----------
+            uint32_t mask_hi = 0;
+            if (__any_sync(0xFFFFFFFFu, mid)) {
+                if (mid) {
+                    Setup s;
+                    s.x1 = x1; s.y1 = y1; s.x2 = x2; s.y2 = y2; s.x3 = x3; s.y3 = y3;
+                    s.dx0 = dx0; s.dy0 = dy0; s.dx1 = dx1; s.dy1 = dy1; s.dx2 = dx2; s.dy2 = dy2;
+                    unsigned long long m = 0ull;
+                    bool open = false;
+                    for (uint32_t r = 0; r < rows && !open; ++r) {
+                        const RowC rc = row_setup(s, miny + r);
+                        bool closed = false;
+                        for (uint32_t k = 0; k < 8u && k < span; ++k) {
+                            float w0, w1, w2;
+                            edge_eval(s, rc, minx + k, w0, w1, w2);
+                            if (!(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f)) m |= 1ull << (r * 8u + k);
+                            else if (row_closed(s, w0, w1, w2)) { closed = true; break; }
+                        }
+                        open = !closed && span > 8u;   // candidates remain right of the window
+                    }
+                    if (open) walk_items = (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw);
+                    else { mask = (uint32_t)m; mask_hi = (uint32_t)(m >> 32); }
+                }
+            }
+
             // ---- phase C: park covering triangles; emit 32 at a time --------------------------
-            const unsigned cov = __ballot_sync(0xFFFFFFFFu, mask != 0u);
+            const unsigned cov = __ballot_sync(0xFFFFFFFFu, (mask | mask_hi) != 0u);
             if (cov) {
-                if (mask) {
+                if (mask | mask_hi) {
                     const uint32_t slot = (q_head + q_count + __popc(cov & ((1u << lane) - 1u))) & (G3_RING - 1u);
                     wq.raw[0][slot] = v0; wq.raw[1][slot] = v1; wq.raw[2][slot] = v2;
                     wq.raw[3][slot] = v3; wq.raw[4][slot] = v4; wq.raw[5][slot] = v5;
                     wq.raw[6][slot] = v6; wq.raw[7][slot] = v7; wq.raw[8][slot] = v8;
-                    wq.tri[slot] = t;
+                    wq.tri[slot] = t | (mid ? 0x80000000u : 0u);
                     wq.xy[slot] = minx | (miny << 16);
-                    wq.mask[slot] = mask;
+                    wq.mask_lo[slot] = mask;
+                    wq.mask_hi[slot] = mask_hi;
                 }
                 q_count += __popc(cov);
                 if (q_count >= 32u) {

@@ -201,3 +201,18 @@ def test_cli_drop_in_image_and_webify(tmp_path):
     out = subprocess.run([exe, obj, "image", "-w", "31"], capture_output=True, check=True).stdout   # -h defaults to -w, colour on
     cells = oracle.render(xyz, white, s0, 31, 31, oracle.rotation(0.0, S.PI, 0.0), mode=0)[0]
     assert out == rs.flush_bytes(cells, True, False, True)
+
+
+def test_band_renderer_single_process():
+    """multigpu.BandRenderer with world=1 (device buffers, external stream) equals the host path."""
+    import torch
+    from rust_sloth_b200 import multigpu
+    xyz, rgb, s0 = S.soup("skull")
+    rot = oracle.rotation(0.0, S.PI, 0.0)
+    ctx = rs.Context.blank(True)
+    ctx.set_scene(xyz, rgb, s0)
+    br = multigpu.BandRenderer(ctx, 320, 200, 0, 1)
+    frame = br.to_frame(br.render(rot))
+    ocells, _, _ = oracle.render(xyz, rgb, s0, 320, 200, rot, mode=0)
+    assert np.array_equal(frame, ocells)
+    ctx.close()
