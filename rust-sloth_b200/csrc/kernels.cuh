@@ -499,9 +499,9 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
     }
 }
 
-// One warp per row-band item.  Lanes take 32 consecutive candidates of a row;
-// a row ends when any lane sees a closing edge fail (everything right of that
-// lane fails as well) or at the reference's maxx.
+// One warp per row-band item.  Lanes take 32 consecutive candidates of a row (or
+// 2 x 16 / 4 x 8 for narrow triangles); a row ends when a lane of that row sees a
+// closing edge fail (everything right of it fails as well) or at the reference's maxx.
 __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ FrameParams p, const Scene sc,
                                               unsigned long long* __restrict__ keys, const Queues q)
 {
@@ -529,16 +529,22 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ FrameParam
         setup_tri(p, v, s);
         Shade sh;
         shade_setup(s, sh);
-        const uint32_t rpi = walk_rows_per_item(tight_width(s));
+        const uint32_t tw = tight_width(s);
+        const uint32_t rpi = walk_rows_per_item(tw);
         const uint32_t y0 = s.miny + band * rpi;
         const uint32_t y1 = min(s.maxy, y0 + rpi);
-        for (uint32_t y = y0; y < y1; ++y) {
-            if (y + 1u < p.krow0 || y >= p.row1) continue;
+        // lanes as (32/cw) rows x cw columns: narrow triangles take several rows per step
+        const uint32_t cw = tw <= 6u ? 8u : (tw <= 14u ? 16u : 32u);
+        const uint32_t lr = lane / cw, lx = lane % cw, rows_per_step = 32u / cw;
+        const uint32_t group = (cw == 32u ? 0xFFFFFFFFu : ((1u << cw) - 1u)) << (lr * cw);
+        for (uint32_t yb = y0; yb < y1; yb += rows_per_step) {
+            const uint32_t y = yb + lr;
+            bool done = !(y < y1 && y + 1u >= p.krow0 && y < p.row1);
             const RowC rc = row_setup(s, y);
-            for (uint32_t xb = s.minx; xb < s.maxx; xb += 32u) {
-                const uint32_t x = xb + lane;
+            for (uint32_t xb = s.minx; xb < s.maxx; xb += cw) {
+                const uint32_t x = xb + lx;
                 bool closed = false;
-                if (x < s.maxx) {
+                if (!done && x < s.maxx) {
                     float w0, w1, w2;
                     edge_eval(s, rc, x, w0, w1, w2);
                     if (w0 >= 0.0f && w1 >= 0.0f && w2 >= 0.0f) {
@@ -548,7 +554,8 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ FrameParam
                         closed = row_closed(s, w0, w1, w2);
                     }
                 }
-                if (__any_sync(0xFFFFFFFFu, closed)) break;
+                if (__ballot_sync(0xFFFFFFFFu, closed) & group) done = true;   // this lane's row is finished
+                if (__all_sync(0xFFFFFFFFu, done)) break;
             }
         }
     }
