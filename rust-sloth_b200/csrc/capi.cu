@@ -92,20 +92,14 @@ struct sloth_ctx {
     float* d_z = nullptr;
     cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
 
-    // queues + per-frame aux (rowbits and FrameAux are one allocation, cleared by one memset)
+    // queues + per-frame aux (rowmax and FrameAux are one allocation, cleared by one memset)
     uint32_t* walk_tri = nullptr;
     unsigned long long* walk_base = nullptr;
     uint32_t* irr_tri = nullptr;
-    uint32_t hull_tile = 32;         // triangles per row-hull record of the last frame
-    uint32_t* tile_hull = nullptr;   // [ceil(n_tri/256)] row hull of each geometry tile
-    int geom_variant = 3;            // SLOTH_GEOM=1 selects the first-generation kernel k_geom (A/B runs)
     uint32_t debug = 0;              // SLOTH_DEBUG bits, profiling experiments only
     bool scene_clean = false;        // every |coordinate| <= 2^20: no per-triangle regularity test needed
     uint8_t* aux_region = nullptr;
-    size_t aux_bytes = 0, rowbits_bytes = 0;
-    uint32_t* fix_rows = nullptr;
-    uint32_t* fix_tri = nullptr;
-    uint32_t* fix_newline = nullptr;
+    size_t aux_bytes = 0, rowmax_bytes = 0;
 
     float thr[9];
     char glyph[10];
@@ -127,14 +121,10 @@ int free_frame_state(sloth_ctx* c)
     cudaFree(c->d_cells[1]);
     cudaFree(c->d_z);
     cudaFree(c->aux_region);
-    cudaFree(c->fix_rows);
-    cudaFree(c->fix_tri);
-    cudaFree(c->fix_newline);
     c->keys = nullptr;
     c->d_cells[0] = c->d_cells[1] = nullptr;
     c->d_z = nullptr;
     c->aux_region = nullptr;
-    c->fix_rows = c->fix_tri = c->fix_newline = nullptr;
     c->sized = false;
     return 0;
 }
@@ -154,13 +144,9 @@ int alloc_frame_state(sloth_ctx* c)
     CU(cudaMalloc(&c->keys, std::max<size_t>(c->n_key_slots, 1) * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(c->keys, 0xFF, std::max<size_t>(c->n_key_slots, 1) * sizeof(unsigned long long), c->stream));
     for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->d_cells[i], (c->cells_per_frame + 2) * sizeof(uint32_t)));
-    c->rowbits_bytes = (((size_t)H + 31) / 32) * 4;
-    c->rowbits_bytes = (c->rowbits_bytes + 8 + 15) & ~(size_t)15;   // + one padding word for the 2-word probe
-    c->aux_bytes = c->rowbits_bytes + sizeof(FrameAux);
+    c->rowmax_bytes = ((((size_t)H + 31) & ~(size_t)31) + 64) * sizeof(uint32_t);
+    c->aux_bytes = c->rowmax_bytes + sizeof(FrameAux);
     CU(cudaMalloc(&c->aux_region, c->aux_bytes));
-    CU(cudaMalloc(&c->fix_rows, (size_t)H * 4 + 4));
-    CU(cudaMalloc(&c->fix_tri, (size_t)H * 4 + 4));
-    CU(cudaMalloc(&c->fix_newline, (size_t)H * 4 + 4));
     c->sized = true;
     return SLOTH_OK;
 }
@@ -203,42 +189,38 @@ int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z
     q.walk_tri = c->walk_tri;
     q.walk_base = c->walk_base;
     q.irr_tri = c->irr_tri;
-    q.rowbits = reinterpret_cast<uint32_t*>(c->aux_region);
-    q.aux = reinterpret_cast<FrameAux*>(c->aux_region + c->rowbits_bytes);
-    q.fix_rows = c->fix_rows;
-    q.fix_tri = c->fix_tri;
-    q.fix_newline = c->fix_newline;
+    q.rowmax = reinterpret_cast<uint32_t*>(c->aux_region);
+    q.aux = reinterpret_cast<FrameAux*>(c->aux_region + c->rowmax_bytes);
     cudaStream_t st = c->stream;
     const bool kt = timed && (c->stat_flags & 2u);
 
     if (timed) CU(cudaEventRecord(c->ev[EV_START], st));
     CU(cudaMemsetAsync(c->aux_region, 0, c->aux_bytes, st));
     if (c->n_tri) {
-        if (c->geom_variant == 1) {
-            k_geom<<<(c->n_tri + 255) / 256, 256, 0, st>>>(p, sc, c->keys, q);
-        } else {
+        {
             const uint32_t n_chunks = (c->n_tri + 31) / 32;
-            // consecutive chunks per warp turn: 16 for big scenes (coherent row stamps, fewer hull records),
-            // fewer when that would leave warps without work
+            // consecutive chunks per warp turn: 16 for big scenes (neighbouring triangles share rows and
+            // cache lines), fewer when that would leave warps without work
             const uint32_t warps_avail = (uint32_t)c->sm_count * 3u * G3_WARPS;
-            uint32_t batch_chunks = std::max<uint32_t>(1u, std::min<uint32_t>(G3_BATCH_MAX, n_chunks / (warps_avail * 4u)));
-            c->hull_tile = batch_chunks * 32u;
+            const uint32_t batch_chunks = std::max<uint32_t>(1u, std::min<uint32_t>(G3_BATCH_MAX, n_chunks / (warps_avail * 4u)));
             const uint32_t n_batches = (n_chunks + batch_chunks - 1) / batch_chunks;
             const uint32_t grid = std::min<uint32_t>((n_batches + G3_WARPS - 1) / G3_WARPS, (uint32_t)c->sm_count * 3u);
             // a clean scene under a bounded matrix cannot produce |x'|,|y'| > 2^40: skip the per-triangle test
             bool bounded = c->scene_clean;
             for (int i = 0; i < 8; ++i) bounded = bounded && std::fabs(p.m[i]) <= 131072.0f;
-            const size_t dyn = (((size_t)c->H + 31) / 32 + 1) * sizeof(uint32_t);   // per-block row-stamp bitmap
+            // per-block row-stamp array in shared memory while 3 blocks/SM still fit (H <= 8192)
+            const uint32_t rowmax_shared = c->rowmax_bytes <= 33024 ? 1u : 0u;
+            const size_t dyn = rowmax_shared ? c->rowmax_bytes : 0;
             const bool band_mode = c->row1 != 0;
             auto kern = bounded ? (band_mode ? k_geom3<false, true> : k_geom3<false, false>)
                                 : (band_mode ? k_geom3<true, true> : k_geom3<true, false>);
-            kern<<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->keys, q, c->tile_hull, batch_chunks);
+            if (dyn > 16384) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            kern<<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->keys, q, batch_chunks, rowmax_shared);
         }
         if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
-        k_walk<<<c->sm_count * 8, 128, 0, st>>>(p, sc, c->keys, q);
-        k_irregular<<<c->sm_count, 256, 0, st>>>(p, sc, c->keys, q);
+        k_tail<<<c->sm_count * 8 + c->sm_count, 128, 0, st>>>(p, sc, c->keys, q, (uint32_t)c->sm_count * 8u);
         if (kt) CU(cudaEventRecord(c->ev[EV_WALK], st));
-        c->launches += 3;
+        c->launches += 2;
     } else if (kt) {
         CU(cudaEventRecord(c->ev[EV_GEOM], st));
         CU(cudaEventRecord(c->ev[EV_WALK], st));
@@ -264,11 +246,6 @@ int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z
         if (n) k_resolve_odd<<<(n + 255) / 256, 256, 0, st>>>(p, sc, c->keys, q, d_out, n_cells, n_tail, c->halo_slots);
         const uint32_t nk = (uint32_t)c->n_key_slots;
         if (nk) k_clear_keys_odd<<<(nk + 255) / 256, 256, 0, st>>>(c->keys, nk);
-        c->launches += 2;
-    }
-    if (c->image && c->n_tri) {
-        k_stampfix_scan<<<c->sm_count * 4, 256, 0, st>>>(p, sc, q, c->tile_hull, c->geom_variant == 1 ? 0u : 1u, c->geom_variant == 1 ? GEOM_TILE : c->hull_tile);
-        k_stampfix_apply<<<1, 256, 0, st>>>(p, q, d_out);
         c->launches += 2;
     }
     if (timed) CU(cudaEventRecord(c->ev[EV_END], st));
@@ -313,10 +290,6 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     if (const char* g = std::getenv("SLOTH_DEBUG")) c->debug = (uint32_t)std::atoi(g);
-    if (const char* g = std::getenv("SLOTH_GEOM")) {
-        const int v = std::atoi(g);
-        if (v == 1) c->geom_variant = 1;
-    }
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
@@ -341,7 +314,6 @@ int sloth_ctx_destroy(sloth_ctx* c)
     cudaFree(c->walk_tri);
     cudaFree(c->walk_base);
     cudaFree(c->irr_tri);
-    cudaFree(c->tile_hull);
     for (int i = 0; i < EV_N; ++i) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) {
         cudaEventDestroy(c->ev_rendered[i]);
@@ -361,8 +333,7 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_c);
-    cudaFree(c->walk_tri); cudaFree(c->walk_base); cudaFree(c->irr_tri); cudaFree(c->tile_hull);
-    c->tile_hull = nullptr;
+    cudaFree(c->walk_tri); cudaFree(c->walk_base); cudaFree(c->irr_tri);
     c->sc_a = c->sc_b = nullptr; c->sc_c = nullptr;
     c->walk_tri = c->irr_tri = nullptr; c->walk_base = nullptr;
     c->have_scene = false;
@@ -373,7 +344,6 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
     CU(cudaMalloc(&c->walk_tri, n * sizeof(uint32_t)));
     CU(cudaMalloc(&c->walk_base, n * sizeof(unsigned long long)));
     CU(cudaMalloc(&c->irr_tri, n * sizeof(uint32_t)));
-    CU(cudaMalloc(&c->tile_hull, ((n + 31) / 32) * sizeof(uint32_t)));
     if (n_tri) {
         float* d_xyz = nullptr;
         uint8_t* d_rgb = nullptr;
@@ -536,12 +506,12 @@ int sloth_stats_get(sloth_ctx* c, sloth_stats* out)
     out->n_tri = c->n_tri;
     if (c->sized && c->aux_region) {
         FrameAux aux;
-        CU(cudaMemcpy(&aux, c->aux_region + c->rowbits_bytes, sizeof aux, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&aux, c->aux_region + c->rowmax_bytes, sizeof aux, cudaMemcpyDeviceToHost));
         out->fragments = aux.frag_counter;
         out->walk_tris = (uint32_t)(aux.walk_counter >> ITEM_BITS);
         out->walk_items = (uint32_t)(aux.walk_counter & ITEM_MASK);
         out->irregular_tris = aux.irr_count;
-        out->stamp_fixups = aux.fix_count;
+        out->stamp_fixups = aux.stamp_exact;
     }
     if (c->ev_valid) {
         if (c->last_was_batch) out->last_frame_ms = c->batch_ms_per_frame;

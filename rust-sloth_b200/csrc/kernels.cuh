@@ -1,35 +1,28 @@
 // kernels.cuh -- the per-frame kernels of the sloth raster path (sm_100a).
 //
-// Frame pipeline (one stream, no host round-trips):
-//   k_geom     one thread per triangle: coalesced 16+16+8 B loads, transform, bounds,
-//              image-mode row stamps; sub-tile triangles are rasterised in place
-//              (64-bit atomicMin into the key plane), larger ones are queued as
-//              row-band work items with one warp-aggregated atomic per warp,
-//              non-finite ones are queued for the brute-force kernel
-//   k_walk     one warp per row-band item: 32 candidates per step, ballot-driven
-//              row termination, atomicMin into the key plane
-//   k_irregular one block per queued triangle: the reference's whole scan domain
-//   k_resolve  key plane -> cell buffer (glyph + colour, double-cell write,
-//              newline stamps), vectorised stores, resets the key plane
-//   k_stampfix_* rare: order between a newline stamp and a wrapped fragment that
-//              lands on the same cell
+// Frame pipeline (one stream, no host round-trips, 3 launches + one small memset):
+//   k_geom3    persistent warps over the triangle stream: coalesced 16+16+8 B loads with register
+//              prefetch, transform, bounds, image-mode row stamps, back-face proof; triangles up to
+//              8x8 candidates are rasterised in place (64-bit atomicMin into the key plane), larger
+//              ones are queued as row-band work items, non-finite ones for the brute-force pass
+//   k_tail     walk part: one warp per row-band item, ballot-terminated rows;
+//              irregular part: the reference's whole scan domain for NaN/inf/huge triangles
+//   k_resolve  key plane -> cell buffer (glyph + colour, double-cell write, newline stamps and
+//              their order against wrapped fragments), 8-byte stores, resets the key plane
 #pragma once
 #include "raster_core.cuh"
 
 namespace sloth {
 
-static constexpr uint32_t TINY_ROWS = 4;   // rows x columns handled inside k_geom
-static constexpr uint32_t TINY_COLS = 4;
-static constexpr uint32_t TINY_MAX_STEPS = TINY_COLS + 3;  // per row before handing over to k_walk
 static constexpr int ITEM_BITS = 37;       // packed queue counter: slots << 37 | items
 static constexpr unsigned long long ITEM_MASK = (1ull << ITEM_BITS) - 1ull;
 
-// Small per-frame device state (cleared with one memset per frame).
+// Small per-frame device state (cleared with one memset per frame, together with rowmax).
 struct FrameAux {
     unsigned long long walk_counter;   // slots << 37 | items
     unsigned long long frag_counter;   // covered fragments (only when count_frags)
     uint32_t irr_count;
-    uint32_t fix_count;
+    uint32_t stamp_exact;              // newline-vs-wrapped-fragment order decided by the exact check
     uint32_t pad[10];
 };
 
@@ -37,129 +30,11 @@ struct Queues {
     uint32_t* __restrict__ walk_tri;             // [n_tri]
     unsigned long long* __restrict__ walk_base;  // [n_tri] first item id of that triangle (ascending)
     uint32_t* __restrict__ irr_tri;              // [n_tri]
-    uint32_t* __restrict__ rowbits;              // [(H+31)/32] image-mode: rows stamped by some triangle
-    uint32_t* __restrict__ fix_rows;             // [H] rows whose column-1 cell needs the order check
-    uint32_t* __restrict__ fix_tri;              // [H] triangle of the wrapped winner on that cell
-    uint32_t* __restrict__ fix_newline;          // [H] 1 if a later stamp overrides it
+    // image mode: rowmax[y] = 1 + index of the last 32-triangle chunk that stamps row y with the
+    // '\n' marker (rasterizer.rs:89-91), 0 = row never stamped.  [H + 64]
+    uint32_t* __restrict__ rowmax;
     FrameAux* __restrict__ aux;
 };
-
-// rows [y0,y1) of a triangle get the '\n' marker at column 1 (rasterizer.rs:89-91).
-SLOTH_DEV void stamp_rows(const FrameParams& p, const Queues& q, uint32_t y0, uint32_t y1)
-{
-    y0 = max(y0, p.row0);
-    y1 = min(y1, p.row1);
-    if (y0 >= y1) return;
-    for (uint32_t w = y0 >> 5; w <= (y1 - 1) >> 5; ++w) {
-        const uint32_t lo = max(y0, w << 5) & 31u, hi = (min(y1, (w + 1) << 5) - 1u) & 31u;
-        const uint32_t m = (0xFFFFFFFFu >> (31u - hi)) & (0xFFFFFFFFu << lo);
-        if ((q.rowbits[w] & m) != m) atomicOr(q.rowbits + w, m);
-    }
-}
-
-__global__ void __launch_bounds__(256) k_geom(const __grid_constant__ FrameParams p, const Scene sc,
-                                              unsigned long long* __restrict__ keys, const Queues q)
-{
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t walk_items = 0;   // > 0: queue this triangle for k_walk
-    bool irregular = false;
-    uint32_t nfrag = 0;
-
-    if (t < p.n_tri) {
-        float v[9];
-        uint32_t rgb;
-        load_tri(sc, t, v, rgb);
-        Setup s;
-        setup_tri(p, v, s);
-        // destination rows are y (direct) or y+1 (wrapped): skip triangles outside the band
-        const bool rows_ok = s.miny < s.maxy && s.miny < p.row1 && s.maxy + 1u > p.krow0;
-        if (rows_ok) {
-            if (p.image) stamp_rows(p, q, s.miny, s.maxy);
-            if (s.minx < s.maxx) {
-                const uint32_t rows = s.maxy - s.miny;
-                const uint32_t tw = tight_width(s);
-                if (!s.regular) {
-                    irregular = true;
-                } else if (rows <= TINY_ROWS && tw <= TINY_COLS) {
-                    Shade sh;
-                    bool have_sh = false;
-                    bool bail = false;
-                    for (uint32_t y = s.miny; y < s.maxy && !bail; ++y) {
-                        const RowC rc = row_setup(s, y);
-                        uint32_t steps = 0;
-                        for (uint32_t x = s.minx; x < s.maxx; ++x) {
-                            float w0, w1, w2;
-                            edge_eval(s, rc, x, w0, w1, w2);
-                            if (w0 >= 0.0f && w1 >= 0.0f && w2 >= 0.0f) {
-                                if (!have_sh) {
-                                    shade_setup(s, sh);
-                                    have_sh = true;
-                                }
-                                emit_fragment(p, s, sh, t, x, y, w0, w1, w2, keys);
-                                ++nfrag;
-                            } else if (row_closed(s, w0, w1, w2)) {
-                                break;
-                            }
-                            if (++steps > TINY_MAX_STEPS) {  // degenerate sliver: let k_walk redo it
-                                bail = true;
-                                break;
-                            }
-                        }
-                    }
-                    if (bail) {
-                        nfrag = 0;  // k_walk re-emits the same keys (atomicMin is idempotent) and recounts
-                        walk_items = (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw);
-                    }
-                } else {
-                    walk_items = (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw);
-                }
-            }
-        }
-    }
-
-    // ---- warp-aggregated queue allocation: one atomic per warp -----------------------
-    const unsigned need = __ballot_sync(0xFFFFFFFFu, walk_items > 0);
-    if (need) {
-        uint32_t incl = walk_items;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if ((int)lane >= d) incl += n;
-        }
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        unsigned long long old = 0;
-        if (lane == 0)
-            old = atomicAdd(&q.aux->walk_counter, ((unsigned long long)__popc(need) << ITEM_BITS) | total);
-        old = __shfl_sync(0xFFFFFFFFu, old, 0);
-        if (walk_items > 0) {
-            const uint32_t slot = (uint32_t)(old >> ITEM_BITS) + __popc(need & ((1u << lane) - 1u));
-            q.walk_tri[slot] = t;
-            q.walk_base[slot] = (old & ITEM_MASK) + (incl - walk_items);
-        }
-    }
-    const unsigned irr = __ballot_sync(0xFFFFFFFFu, irregular);
-    if (irr) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&q.aux->irr_count, (uint32_t)__popc(irr));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (irregular) q.irr_tri[base + __popc(irr & ((1u << lane) - 1u))] = t;
-    }
-    if (p.count_frags) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) nfrag += __shfl_xor_sync(0xFFFFFFFFu, nfrag, d);
-        if (lane == 0 && nfrag) atomicAdd(&q.aux->frag_counter, (unsigned long long)nfrag);
-    }
-}
-
-SLOTH_DEV uint32_t row_mask_in_word(uint32_t y0, uint32_t y1, uint32_t w)
-{
-    const uint32_t lo = max(y0, w << 5), hi = min(y1, (w + 1u) << 5);
-    if (lo >= hi) return 0u;
-    return (0xFFFFFFFFu >> (32u - (hi - lo))) << (lo & 31u);
-}
-
-static constexpr uint32_t GEOM_TILE = 256;   // triangles per block of the first-generation kernel
 
 // ---------------------------------------------------------------------------------
 // k_geom3: the geometry kernel, warp-autonomous (no block barriers).
@@ -261,7 +136,7 @@ SLOTH_DEV void g3_emit(const FrameParams& p, const G3Queue& wq, uint32_t head, u
 template <bool CHECK_REGULAR, bool BAND>
 __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constant__ FrameParams p, const Scene sc,
                                                             unsigned long long* __restrict__ keys, const Queues q,
-                                                            uint32_t* __restrict__ batch_hull, const uint32_t batch_chunks)
+                                                            const uint32_t batch_chunks, const uint32_t rowmax_shared)
 {
     __shared__ G3Queue queues[G3_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -271,10 +146,14 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
     const uint32_t n_warps = gridDim.x * G3_WARPS;
     uint32_t q_head = 0, q_count = 0, nfrag_count = 0;   // warp-uniform ring state
     const bool do_stamps = p.image && !(p.debug & 2u);
-    extern __shared__ uint32_t s_rowbits[];   // (H+31)/32 + 1 words: rows stamped by this block
-    const uint32_t n_row_words = ((p.H + 31u) >> 5) + 1u;
-    if (do_stamps) {
-        for (uint32_t i = threadIdx.x; i < n_row_words; i += blockDim.x) s_rowbits[i] = 0u;
+    // Row stamps: per-block copy of rowmax in shared memory (every warp in flight stamps the same
+    // few rows, and same-address traffic serialises in L2); flushed once at the end.  Frames taller
+    // than the shared-memory budget (rowmax_shared == 0) stamp the global array directly.
+    extern __shared__ uint32_t s_rowmax_buf[];
+    const uint32_t n_rowmax = ((p.H + 31u) & ~31u) + 64u;
+    uint32_t* const rowmax = rowmax_shared ? s_rowmax_buf : q.rowmax;
+    if (do_stamps && rowmax_shared) {
+        for (uint32_t i = threadIdx.x; i < n_rowmax; i += blockDim.x) s_rowmax_buf[i] = 0u;
         __syncthreads();
     }
 
@@ -287,7 +166,6 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
     }
     for (; batch < n_batches; batch += n_warps) {
         const uint32_t c_end = min(n_chunks, (batch + 1u) * batch_chunks);
-        uint32_t hull_lo = 0xFFFFFFFFu, hull_hi = 0u;   // per-lane row hull of this batch (for k_stampfix_scan)
         for (uint32_t c = batch * batch_chunks; c < c_end; ++c) {
             const uint32_t t = c * 32u + lane;
             const float v0 = A.x, v1 = A.y, v2 = A.z, v3 = A.w, v4 = B.x, v5 = B.y, v6 = B.z, v7 = B.w, v8 = C.x;
@@ -310,29 +188,26 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
             // rows (y, or y+1 after a row wrap) miss the band
             const bool has_rows = t < p.n_tri && miny < maxy && (!BAND || (miny < p.row1 && maxy + 1u > p.krow0));
 
-            // ---- row stamps (rasterizer.rs:89-91) + row hull of the batch ---------------------
-            // Stamps go to a per-block bitmap in shared memory (flushed once at the end): every
-            // warp in flight stamps the same few rows, and same-address traffic serialises in L2.
+            // ---- row stamps (rasterizer.rs:89-91) ----------------------------------------------
+            // rowmax[y] = max(c + 1) over chunks c that stamp row y.  The lanes of a chunk are
+            // neighbours on screen, so their rows fall into a 64-row window: two REDUX.OR give
+            // the chunk's row set, then lane i owns rows i and 32+i of the window (conflict-free).
             if (do_stamps) {
                 const uint32_t sy0 = BAND ? max(miny, p.row0) : miny, sy1 = BAND ? min(maxy, p.row1) : maxy;
                 const bool st = has_rows && sy0 < sy1;
-                if (has_rows) { hull_lo = min(hull_lo, miny); hull_hi = max(hull_hi, maxy); }   // reduced once per batch
                 const uint32_t ymin = __reduce_min_sync(0xFFFFFFFFu, st ? sy0 : 0xFFFFFFFFu);
                 if (ymin != 0xFFFFFFFFu) {
-                    const uint32_t wmin = ymin >> 5;
-                    const uint32_t lo = sy0 - (wmin << 5), n = sy1 - sy0;   // meaningful when st
+                    const uint32_t base = ymin & ~31u;
+                    const uint32_t lo = sy0 - base, n = sy1 - sy0;          // meaningful when st
                     const bool fits = st && n <= 32u && lo + n <= 64u;      // inside the 2-word window
                     unsigned long long m64 = 0ull;
                     if (fits) m64 = (unsigned long long)(0xFFFFFFFFu >> (32u - n)) << lo;
                     const uint32_t need0 = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)m64);
                     const uint32_t need1 = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(m64 >> 32));
-                    if (lane < 2u) {
-                        const uint32_t mine = lane == 0 ? need0 : need1;
-                        if (mine) atomicOr(s_rowbits + wmin + lane, mine);
-                    }
-                    if (st && !fits)   // tall or far-away triangle: word by word
-                        for (uint32_t w = sy0 >> 5; w <= (sy1 - 1u) >> 5; ++w)
-                            atomicOr(s_rowbits + w, row_mask_in_word(sy0, sy1, w));
+                    if ((need0 >> lane) & 1u) atomicMax(rowmax + base + lane, c + 1u);
+                    if ((need1 >> lane) & 1u) atomicMax(rowmax + base + 32u + lane, c + 1u);
+                    if (st && !fits)   // tall or far-away triangle: row by row
+                        for (uint32_t y = sy0; y < sy1; ++y) atomicMax(rowmax + y, c + 1u);
                 }
             }
 
@@ -475,21 +350,16 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
                 }
             }
         }
-        if (do_stamps) {
-            const uint32_t hmin = __reduce_min_sync(0xFFFFFFFFu, hull_lo);
-            const uint32_t hmax = __reduce_max_sync(0xFFFFFFFFu, hull_hi);
-            if (lane == 0) batch_hull[batch] = hmin == 0xFFFFFFFFu ? 0u : (hmin | (hmax << 16));
-        }
     }
     if (q_count) {
         __syncwarp();
         g3_emit(p, wq, q_head, q_count, lane, keys, nfrag_count);
     }
-    if (do_stamps) {   // publish this block's stamped rows
+    if (do_stamps && rowmax_shared) {   // publish this block's stamps (the probe skips most atomics)
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n_row_words - 1u; i += blockDim.x) {
-            const uint32_t m = s_rowbits[i];
-            if (m && (__ldcg(q.rowbits + i) & m) != m) atomicOr(q.rowbits + i, m);
+        for (uint32_t i = threadIdx.x; i < n_rowmax - 64u; i += blockDim.x) {
+            const uint32_t m = s_rowmax_buf[i];
+            if (m && __ldcg(q.rowmax + i) < m) atomicMax(q.rowmax + i, m);
         }
     }
     if (p.count_frags) {
@@ -502,15 +372,15 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
 // One warp per row-band item.  Lanes take 32 consecutive candidates of a row (or
 // 2 x 16 / 4 x 8 for narrow triangles); a row ends when a lane of that row sees a
 // closing edge fail (everything right of it fails as well) or at the reference's maxx.
-__global__ void __launch_bounds__(128) k_walk(const __grid_constant__ FrameParams p, const Scene sc,
-                                              unsigned long long* __restrict__ keys, const Queues q)
+SLOTH_DEV void walk_body(const FrameParams& p, const Scene& sc, unsigned long long* __restrict__ keys, const Queues& q,
+                         uint32_t n_blocks)
 {
     const unsigned long long packed = q.aux->walk_counter;
     const unsigned long long n_items = packed & ITEM_MASK;
     const uint32_t n_slots = (uint32_t)(packed >> ITEM_BITS);
     if (n_items == 0) return;
     const uint32_t lane = threadIdx.x & 31u;
-    const unsigned long long n_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    const unsigned long long n_warps = (unsigned long long)n_blocks * (blockDim.x >> 5);
     uint32_t nfrag = 0;
     for (unsigned long long item = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
          item < n_items; item += n_warps) {
@@ -568,12 +438,12 @@ __global__ void __launch_bounds__(128) k_walk(const __grid_constant__ FrameParam
 
 // Triangles with NaN/inf/huge coordinates: no monotonicity argument applies,
 // so every candidate of the reference's scan domain is evaluated.
-__global__ void __launch_bounds__(256) k_irregular(const __grid_constant__ FrameParams p, const Scene sc,
-                                                   unsigned long long* __restrict__ keys, const Queues q)
+SLOTH_DEV void irregular_body(const FrameParams& p, const Scene& sc, unsigned long long* __restrict__ keys,
+                              const Queues& q, uint32_t block, uint32_t n_blocks)
 {
     const uint32_t n = q.aux->irr_count;
     uint32_t nfrag = 0;
-    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    for (uint32_t i = block; i < n; i += n_blocks) {
         const uint32_t t = q.irr_tri[i];
         float v[9];
         uint32_t rgb;
@@ -597,6 +467,16 @@ __global__ void __launch_bounds__(256) k_irregular(const __grid_constant__ Frame
     if (p.count_frags && nfrag) atomicAdd(&q.aux->frag_counter, (unsigned long long)nfrag);
 }
 
+// One launch for both follow-up passes: blocks [0, walk_blocks) walk the queued row bands,
+// the remaining blocks take the irregular triangles.  Both queues are usually empty or tiny.
+__global__ void __launch_bounds__(128) k_tail(const __grid_constant__ FrameParams p, const Scene sc,
+                                              unsigned long long* __restrict__ keys, const Queues q,
+                                              const uint32_t walk_blocks)
+{
+    if (blockIdx.x < walk_blocks) walk_body(p, sc, keys, q, walk_blocks);
+    else irregular_body(p, sc, keys, q, blockIdx.x - walk_blocks, gridDim.x - walk_blocks);
+}
+
 // ---------------------------------------------------------------------------------
 // Resolve: key plane -> cells.
 // ---------------------------------------------------------------------------------
@@ -609,16 +489,42 @@ SLOTH_DEV uint32_t cell_of(const FrameParams& p, const Scene& sc, unsigned long 
     return (uint32_t)(uint8_t)p.glyph[g] | (rgb << 8);
 }
 
-// Column-1 cell of a stamped row on which a (wrapped) fragment also landed: the
-// stamp of triangle T is written after all fragments of triangles <= T, so the
-// '\n' stays unless the fragment's triangle is later than every stamping triangle.
-// That needs max{T : row in T's y-range}; queue the row, k_stampfix_scan decides.
-SLOTH_DEV void queue_fix(const Queues& q, uint32_t row, uint32_t tri)
+// Column-1 cell of a stamped row on which a (wrapped) fragment also landed: the stamp of
+// triangle T is written after all fragments of triangles <= T (the fragment comes from source
+// row y-1, the stamp follows row y of the same triangle), so the cell shows '\n' unless the
+// fragment's triangle is later than EVERY triangle that stamps the row.  rowmax gives the last
+// stamping chunk; only when the fragment's triangle sits in that very chunk are its 32
+// triangles looked at (one per lane).  All 32 lanes must call this; returns true where the
+// newline wins.
+SLOTH_DEV bool stamp_beats_fragment(const FrameParams& p, const Scene& sc, const Queues& q, bool contested,
+                                    uint32_t row, uint32_t tri)
 {
-    const uint32_t i = atomicAdd(&q.aux->fix_count, 1u);
-    q.fix_rows[i] = row;
-    q.fix_tri[i] = tri;
-    q.fix_newline[i] = 0u;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t last = 0u;
+    if (contested) last = q.rowmax[row] - 1u;             // contested implies the row is stamped
+    bool newline = contested && last > (tri >> 5);
+    unsigned exact = __ballot_sync(0xFFFFFFFFu, contested && last == (tri >> 5));
+    while (exact) {
+        const int src = __ffs(exact) - 1;
+        exact &= exact - 1u;
+        const uint32_t r = __shfl_sync(0xFFFFFFFFu, row, src), tw = __shfl_sync(0xFFFFFFFFu, tri, src);
+        const uint32_t t = (tw & ~31u) + lane;            // the 32 triangles of that chunk
+        bool hit = false;
+        if (t >= tw && t < p.n_tri) {
+            float v[9];
+            uint32_t rgb;
+            load_tri(sc, t, v, rgb);
+            Setup s;
+            setup_tri(p, v, s);
+            hit = r >= s.miny && r < s.maxy;
+        }
+        const bool any = __any_sync(0xFFFFFFFFu, hit);
+        if ((int)lane == src) {
+            newline = any;
+            atomicAdd(&q.aux->stamp_exact, 1u);
+        }
+    }
+    return newline;
 }
 
 // W even: ids are even, one key slot owns cells (2k, 2k+1) of its row.
@@ -629,16 +535,22 @@ __global__ void __launch_bounds__(256) k_resolve_even(const __grid_constant__ Fr
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t blank = (uint32_t)' ';
+    unsigned long long key = KEY_EMPTY;
+    uint32_t c0 = blank, c1 = blank, row = 0;
+    bool stamped = false;
     if (i < n_slots) {
-        const unsigned long long key = keys[i];
+        key = keys[i];
         keys[i] = KEY_EMPTY;  // the key plane is clean again for the next frame
-        uint32_t c0 = blank, c1 = blank;
         if (key != KEY_EMPTY) c0 = c1 = cell_of(p, sc, key);
-        const uint32_t row = p.row0 + i / p.KW, kx = i % p.KW;
-        if (p.image && kx == 0 && ((q.rowbits[row >> 5] >> (row & 31u)) & 1u)) {
-            if (key != KEY_EMPTY) queue_fix(q, row, key_tri(key));  // provisional: fragment stays
-            else c1 = (uint32_t)'\n';
-        }
+        row = p.row0 + i / p.KW;
+        stamped = p.image && i % p.KW == 0u && q.rowmax[row] != 0u;   // this slot owns cells (row,0),(row,1)
+    }
+    if (p.image) {   // warp-uniform; the order check is warp-cooperative
+        const bool contested = stamped && key != KEY_EMPTY;
+        const bool nl = stamp_beats_fragment(p, sc, q, contested, row, key_tri(key));
+        if (stamped && (!contested || nl)) c1 = (uint32_t)'\n';
+    }
+    if (i < n_slots) {
         reinterpret_cast<uint2*>(cells)[i] = make_uint2(c0, c1);
     } else if (i < n_slots + n_tail) {
         cells[2u * n_slots + (i - n_slots)] = blank;  // image-mode tail, context.rs:38-39
@@ -670,21 +582,26 @@ __global__ void __launch_bounds__(256) k_resolve_odd(const __grid_constant__ Fra
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t blank = (uint32_t)' ';
+    unsigned long long kw = KEY_EMPTY;
+    uint32_t c = blank, row = 0;
+    bool stamped = false;
     if (i < n_cells) {
         const uint32_t id = p.row0 * p.W + i;  // global cell index
         const unsigned long long ka = keys[halo + i];
         const unsigned long long kb = (halo + i) > 0 ? keys[halo + i - 1] : KEY_EMPTY;
-        unsigned long long kw = KEY_EMPTY;
         if (ka != KEY_EMPTY && kb != KEY_EMPTY) kw = frag_later(p, ka, id, kb, id - 1u) ? ka : kb;
         else if (ka != KEY_EMPTY) kw = ka;
         else if (kb != KEY_EMPTY) kw = kb;
-        uint32_t c = blank;
         if (kw != KEY_EMPTY) c = cell_of(p, sc, kw);
-        const uint32_t row = id / p.W, col = id % p.W;
-        if (p.image && col == 1 && ((q.rowbits[row >> 5] >> (row & 31u)) & 1u)) {
-            if (kw != KEY_EMPTY) queue_fix(q, row, key_tri(kw));
-            else c = (uint32_t)'\n';
-        }
+        row = id / p.W;
+        stamped = p.image && id % p.W == 1u && q.rowmax[row] != 0u;
+    }
+    if (p.image) {
+        const bool contested = stamped && kw != KEY_EMPTY;
+        const bool nl = stamp_beats_fragment(p, sc, q, contested, row, key_tri(kw));
+        if (stamped && (!contested || nl)) c = (uint32_t)'\n';
+    }
+    if (i < n_cells) {
         cells[i] = c;
     } else if (i < n_cells + n_tail) {
         cells[i] = blank;
@@ -695,51 +612,6 @@ __global__ void __launch_bounds__(256) k_clear_keys_odd(unsigned long long* __re
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keys[i] = KEY_EMPTY;
-}
-
-// For every queued row: does a triangle with index >= the fragment's triangle stamp
-// that row?  One warp per tile of 256 triangles; the tile's row hull (written by
-// k_geom2) rejects almost every tile without touching its triangles.
-__global__ void __launch_bounds__(256) k_stampfix_scan(const __grid_constant__ FrameParams p, const Scene sc,
-                                                       const Queues q, const uint32_t* __restrict__ tile_hull,
-                                                       const uint32_t use_hull, const uint32_t hull_tile)
-{
-    const uint32_t n_fix = q.aux->fix_count;
-    if (n_fix == 0) return;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_tiles = (p.n_tri + hull_tile - 1u) / hull_tile;
-    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles; tile += n_warps) {
-        const uint32_t hull = use_hull ? tile_hull[tile] : 0xFFFF0000u;
-        const uint32_t hmin = hull & 0xFFFFu, hmax = hull >> 16;
-        const uint32_t t_last = min(p.n_tri, (tile + 1u) * hull_tile) - 1u;
-        bool cand = false;   // any still-undecided entry this tile could decide?
-        for (uint32_t i = lane; i < n_fix; i += 32u) {
-            const uint32_t row = q.fix_rows[i];
-            cand = cand || (t_last >= q.fix_tri[i] && row >= hmin && row < hmax && __ldcg(q.fix_newline + i) == 0u);
-        }
-        if (!__any_sync(0xFFFFFFFFu, cand)) continue;
-        for (uint32_t t = tile * hull_tile + lane; t <= t_last; t += 32u) {
-            float v[9];
-            uint32_t rgb;
-            load_tri(sc, t, v, rgb);
-            Setup s;
-            setup_tri(p, v, s);
-            if (s.miny >= s.maxy) continue;
-            for (uint32_t i = 0; i < n_fix; ++i) {
-                const uint32_t row = q.fix_rows[i];
-                if (t >= q.fix_tri[i] && row >= s.miny && row < s.maxy) q.fix_newline[i] = 1u;
-            }
-        }
-    }
-}
-
-__global__ void k_stampfix_apply(const __grid_constant__ FrameParams p, const Queues q,
-                                 uint32_t* __restrict__ cells)
-{
-    const uint32_t n_fix = q.aux->fix_count;
-    for (uint32_t i = threadIdx.x; i < n_fix; i += blockDim.x)
-        if (q.fix_newline[i]) cells[(q.fix_rows[i] - p.row0) * p.W + 1u] = (uint32_t)'\n';
 }
 
 // Context.z_buffer (context.rs:17) reconstructed from the key plane, before resolve.

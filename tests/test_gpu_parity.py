@@ -216,3 +216,32 @@ def test_band_renderer_single_process():
     ocells, _, _ = oracle.render(xyz, rgb, s0, 320, 200, rot, mode=0)
     assert np.array_equal(frame, ocells)
     ctx.close()
+
+
+def test_newline_stamp_vs_wrapped_fragment_order():
+    """A fragment that wraps onto column 0/1 of a stamped row (2x == W or W+1): the cell shows the
+    fragment only if its triangle is later than every triangle stamping that row."""
+    rot = np.eye(4, dtype=np.float32).reshape(16)
+    hits = 0
+    for W, H in [(40, 20), (41, 21), (64, 48), (63, 47)]:
+        for seed in range(30):
+            rng = np.random.default_rng(1000 + seed)
+            n = 40
+            # triangles straddling x_screen = W/2 (object x around +1 with scene_max = 1) on many rows
+            c = np.stack([rng.uniform(0.7, 1.3, n), rng.uniform(-0.9, 0.9, n), rng.uniform(-1, 1, n)], axis=1)
+            xyz = (c[:, None, :] + rng.uniform(-0.25, 0.25, (n, 3, 3))).reshape(n, 9).astype(np.float32)
+            rgb = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+            ocells, oz, _ = oracle.render(xyz, rgb, 1.0, W, H, rot, mode=0)
+            cells, z, st = gpu_frame(xyz, rgb, np.float32(1.0), W, H, rot)
+            assert_same(cells, z, ocells, oz, f"stamp order {W}x{H} seed={seed}")
+            hits += st["stamp_fixups"]
+    assert hits > 0   # the exact same-chunk check was exercised
+
+
+def test_tall_frame_uses_global_row_stamps():
+    xyz, rgb, s0 = S.soup("suzy")
+    rot = oracle.rotation(0.0, S.PI, 0.0)
+    W, H = 16, 9000   # H > 8192: the row-stamp array no longer fits in shared memory
+    ocells, oz, _ = oracle.render(xyz, rgb, s0, W, H, rot, mode=1)
+    cells, z, _ = gpu_frame(xyz, rgb, s0, W, H, rot)
+    assert_same(cells, z, ocells, oz, "tall frame")
