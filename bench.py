@@ -15,7 +15,7 @@ frame: update + clear + draw_mesh over the whole scene (main.rs:78-83).
 * e2e       the same frames through the public C-ABI call with HOST buffers
             (sloth_render_batch: per frame the rotation goes host->device, the cell buffer comes
             back device->host into pinned memory), wall clock, max over ranks.
-* roofline  dominant kernel k_geom (reads the whole scene): algorithmic 40 B/triangle / its average
+* roofline  dominant kernel k_geom3 (reads the whole scene): algorithmic 40 B/triangle / its average
             duration (CUDA events recorded inside the library around that kernel, one frame per
             sample, same frames as the timed region) against the measured HBM peak.
 * cpu_baseline / --impl reference: the CPU oracle (oracle/sloth_oracle.c, a port: the Rust reference
@@ -137,7 +137,9 @@ def run_reference(args, rank, world):
     xyz, rgb, s0 = make_scene(args.freq)
     rots = rotations(TURNTABLE_FRAMES)
     threads = max(1, len(os.sched_getaffinity(0)))
-    stride, t_clear = cpu_sample(xyz, rgb, s0, rots[0], target_s=args.ref_step_seconds)
+    # one step = one frame sample per thread; size it so that warmup+steps stay within ~2.5 minutes
+    step_target = min(args.ref_step_seconds, 150.0 / max(1, args.steps + args.warmup))
+    stride, t_clear = cpu_sample(xyz, rgb, s0, rots[0], target_s=step_target)
     log(f"[bench/reference] {threads} threads, every {stride}-th triangle per frame sample, clear {t_clear * 1e3:.0f} ms")
 
     def one(i):
@@ -275,7 +277,7 @@ def run_b200(args, rank, local_rank, world):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("k_geom_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("k_geom3_dram_bytes_per_launch")
         fps = K * world / (dev_ms_max * 1e-3)
         e2e_fps = K * world / (e2e_ms_max * 1e-3)
         line = {
@@ -290,13 +292,13 @@ def run_b200(args, rank, local_rank, world):
                        "sharding": "independent frames per GPU, no collective" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": cpf * 4,
                     "gfragments_per_s": frags_per_frame * e2e_fps / 1e9},
-            "roofline": {"bound": "hbm", "kernel": "k_geom", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_geom3", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": 40 * n_tri, "avg_launch_ms": g_ms,
                          "frame_bytes": 40 * n_tri + 4 * WIDTH * HEIGHT,
                          "frame_frac": (40.0 * n_tri + 4.0 * WIDTH * HEIGHT) / (dev_ms_max / K * 1e-3) / 1e9 / hbm_peak,
-                         "kernel_ms": {"k_geom": g_ms, "k_walk+k_irregular": float(np.mean(walk_ms)),
-                                       "k_resolve+stampfix": float(np.mean(resolve_ms)),
+                         "kernel_ms": {"k_geom3": g_ms, "k_tail": float(np.mean(walk_ms)),
+                                       "k_resolve": float(np.mean(resolve_ms)),
                                        "frame": float(np.mean(frame_ms))}},
             "gpu_launches": int(launches_timed),
             "clocks": clk.summary(t_wall0, t_wall1),
