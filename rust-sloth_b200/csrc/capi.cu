@@ -76,6 +76,8 @@ struct sloth_ctx {
     float4* sc_a = nullptr;
     float4* sc_b = nullptr;
     float2* sc_c = nullptr;
+    float* sc_chunks = nullptr;      // TMA feed: 1280-byte chunks of 32 triangles
+    bool tma_feed = false;           // SLOTH_TMA=1 feeds k_geom3 through cp.async.bulk + mbarrier (measured 3 % slower)
     uint32_t n_tri = 0;
     float scene_max = 0.0f;
     bool have_scene = false;
@@ -208,14 +210,19 @@ int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z
             // a clean scene under a bounded matrix cannot produce |x'|,|y'| > 2^40: skip the per-triangle test
             bool bounded = c->scene_clean;
             for (int i = 0; i < 8; ++i) bounded = bounded && std::fabs(p.m[i]) <= 131072.0f;
-            // per-block row-stamp array in shared memory while 3 blocks/SM still fit (H <= 8192)
-            const uint32_t rowmax_shared = c->rowmax_bytes <= 33024 ? 1u : 0u;
-            const size_t dyn = rowmax_shared ? c->rowmax_bytes : 0;
+            // per-block row-stamp array in shared memory while 3 blocks/SM still fit
+            const bool tma = c->tma_feed;
+            const size_t ring_bytes = tma ? sizeof(TmaRing) * G3_WARPS : 0;
+            const uint32_t rowmax_shared = c->rowmax_bytes <= (tma ? 17664u : 33024u) ? 1u : 0u;
+            const size_t dyn = ring_bytes + (rowmax_shared ? c->rowmax_bytes : 0);
             const bool band_mode = c->row1 != 0;
-            auto kern = bounded ? (band_mode ? k_geom3<false, true> : k_geom3<false, false>)
-                                : (band_mode ? k_geom3<true, true> : k_geom3<true, false>);
+            void (*kern)(FrameParams, Scene, const float*, unsigned long long*, Queues, uint32_t, uint32_t);
+            if (tma) kern = bounded ? (band_mode ? k_geom3<false, true, true> : k_geom3<false, false, true>)
+                                    : (band_mode ? k_geom3<true, true, true> : k_geom3<true, false, true>);
+            else kern = bounded ? (band_mode ? k_geom3<false, true, false> : k_geom3<false, false, false>)
+                                : (band_mode ? k_geom3<true, true, false> : k_geom3<true, false, false>);
             if (dyn > 16384) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            kern<<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->keys, q, batch_chunks, rowmax_shared);
+            kern<<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->sc_chunks, c->keys, q, batch_chunks, rowmax_shared);
         }
         if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
         k_tail<<<c->sm_count * 8 + c->sm_count, 128, 0, st>>>(p, sc, c->keys, q, (uint32_t)c->sm_count * 8u);
@@ -290,6 +297,7 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     if (const char* g = std::getenv("SLOTH_DEBUG")) c->debug = (uint32_t)std::atoi(g);
+    if (const char* g = std::getenv("SLOTH_TMA")) c->tma_feed = std::atoi(g) != 0;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
@@ -311,6 +319,7 @@ int sloth_ctx_destroy(sloth_ctx* c)
     cudaFree(c->sc_a);
     cudaFree(c->sc_b);
     cudaFree(c->sc_c);
+    cudaFree(c->sc_chunks);
     cudaFree(c->walk_tri);
     cudaFree(c->walk_base);
     cudaFree(c->irr_tri);
@@ -332,7 +341,8 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
     if (n_tri > MAX_TRIS) return fail(SLOTH_E_TOO_LARGE, "%zu triangles; the depth key holds a 27-bit index (max %u)", n_tri, MAX_TRIS);
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_c);
+    cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_c); cudaFree(c->sc_chunks);
+    c->sc_chunks = nullptr;
     cudaFree(c->walk_tri); cudaFree(c->walk_base); cudaFree(c->irr_tri);
     c->sc_a = c->sc_b = nullptr; c->sc_c = nullptr;
     c->walk_tri = c->irr_tri = nullptr; c->walk_base = nullptr;
@@ -341,6 +351,8 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
     CU(cudaMalloc(&c->sc_a, n * sizeof(float4)));
     CU(cudaMalloc(&c->sc_b, n * sizeof(float4)));
     CU(cudaMalloc(&c->sc_c, n * sizeof(float2)));
+    const size_t n_padded = (n + 31) & ~(size_t)31;
+    CU(cudaMalloc(&c->sc_chunks, n_padded / 32 * CHUNK_BYTES));
     CU(cudaMalloc(&c->walk_tri, n * sizeof(uint32_t)));
     CU(cudaMalloc(&c->walk_base, n * sizeof(unsigned long long)));
     CU(cudaMalloc(&c->irr_tri, n * sizeof(uint32_t)));
@@ -352,7 +364,8 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
         CU(cudaMemcpyAsync(d_xyz, xyz, n_tri * 9 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(d_rgb, rgb, n_tri * 3, cudaMemcpyHostToDevice, c->stream));
         k_pack_scene<<<(unsigned)((n_tri + 255) / 256), 256, 0, c->stream>>>(d_xyz, d_rgb, (uint32_t)n_tri, c->sc_a, c->sc_b, c->sc_c);
-        c->launches += 1;
+        k_pack_chunks<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(c->sc_a, c->sc_b, c->sc_c, (uint32_t)n_tri, (uint32_t)n_padded, c->sc_chunks);
+        c->launches += 2;
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(c->stream));
         cudaFree(d_xyz);

@@ -37,6 +37,50 @@ struct Queues {
 };
 
 // ---------------------------------------------------------------------------------
+// TMA feed for k_geom3: the scene is also kept as 1280-byte chunks of 32 triangles
+// ([32 x float4 A][32 x float4 B][32 x float2 C], same fields as Scene), so one elected
+// lane moves a whole chunk with a single cp.async.bulk into a per-warp 3-stage ring and the
+// warp waits on the stage's mbarrier: no per-lane address arithmetic or predicates, no
+// registers held by loads in flight, two chunks of look-ahead.
+// ---------------------------------------------------------------------------------
+static constexpr uint32_t CHUNK_FLOATS = 320;               // 128 + 128 + 64
+static constexpr uint32_t CHUNK_BYTES = CHUNK_FLOATS * 4;   // 1280
+static constexpr uint32_t TMA_STAGES = 3;
+
+SLOTH_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+SLOTH_DEV void mbar_init(unsigned long long* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+SLOTH_DEV void tma_load_chunk(float* dst, const float* src, unsigned long long* bar)
+{
+    // generic-proxy reads of this stage (its previous use) are ordered before the async-proxy write
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(CHUNK_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(CHUNK_BYTES), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+SLOTH_DEV void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+}
+
+struct TmaRing {
+    float stage[TMA_STAGES][CHUNK_FLOATS];
+    unsigned long long full[TMA_STAGES];
+    unsigned long long pad;
+};
+
+// ---------------------------------------------------------------------------------
 // k_geom3: the geometry kernel, warp-autonomous (no block barriers).
 //
 // Persistent warps walk the triangle stream in batches of 16 consecutive chunks of
@@ -133,8 +177,9 @@ SLOTH_DEV void g3_emit(const FrameParams& p, const G3Queue& wq, uint32_t head, u
     }
 }
 
-template <bool CHECK_REGULAR, bool BAND>
+template <bool CHECK_REGULAR, bool BAND, bool TMA>
 __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constant__ FrameParams p, const Scene sc,
+                                                            const float* __restrict__ chunks,
                                                             unsigned long long* __restrict__ keys, const Queues q,
                                                             const uint32_t batch_chunks, const uint32_t rowmax_shared)
 {
@@ -142,37 +187,61 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     G3Queue& wq = queues[warp];
     const uint32_t n_chunks = (p.n_tri + 31u) >> 5;
-    const uint32_t n_batches = (n_chunks + batch_chunks - 1u) / batch_chunks;
     const uint32_t n_warps = gridDim.x * G3_WARPS;
+    const uint32_t gw = blockIdx.x * G3_WARPS + warp;
     uint32_t q_head = 0, q_count = 0, nfrag_count = 0;   // warp-uniform ring state
     const bool do_stamps = p.image && !(p.debug & 2u);
     // Row stamps: per-block copy of rowmax in shared memory (every warp in flight stamps the same
     // few rows, and same-address traffic serialises in L2); flushed once at the end.  Frames taller
     // than the shared-memory budget (rowmax_shared == 0) stamp the global array directly.
-    extern __shared__ uint32_t s_rowmax_buf[];
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    TmaRing* const rings = reinterpret_cast<TmaRing*>(dyn_smem);
+    uint32_t* const s_rowmax_buf = reinterpret_cast<uint32_t*>(dyn_smem + (TMA ? sizeof(TmaRing) * G3_WARPS : 0));
     const uint32_t n_rowmax = ((p.H + 31u) & ~31u) + 64u;
     uint32_t* const rowmax = rowmax_shared ? s_rowmax_buf : q.rowmax;
-    if (do_stamps && rowmax_shared) {
+    if (do_stamps && rowmax_shared)
         for (uint32_t i = threadIdx.x; i < n_rowmax; i += blockDim.x) s_rowmax_buf[i] = 0u;
-        __syncthreads();
+    if (TMA && lane == 0) {
+        for (uint32_t k = 0; k < TMA_STAGES; ++k) mbar_init(&rings[warp].full[k], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
 
-    uint32_t batch = blockIdx.x * G3_WARPS + warp;
+    // This warp's chunks: batches of `batch_chunks` consecutive chunks, batches strided by n_warps.
+    // Two cursors walk that sequence without divisions: `c` (consumed now) and `pf` (being fetched).
+    const uint32_t batch_jump = (n_warps - 1u) * batch_chunks + 1u;
+    uint32_t c = gw * batch_chunks, c_pos = 0;
+    uint32_t pf = c, pf_pos = 0;
+    auto advance = [&](uint32_t& idx, uint32_t& pos) {
+        if (++pos == batch_chunks) { pos = 0; idx += batch_jump; } else ++idx;
+    };
+    TmaRing& ring = rings[TMA ? warp : 0];
     float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
     float2 C = make_float2(0.f, 0.f);
-    if (batch < n_batches && batch * (batch_chunks * 32u) + lane < p.n_tri) {
-        const uint32_t t0 = batch * (batch_chunks * 32u) + lane;
-        A = __ldg(sc.a + t0); B = __ldg(sc.b + t0); C = __ldg(sc.c + t0);
+    if (TMA) {
+        for (uint32_t k = 0; k < TMA_STAGES; ++k) {
+            if (lane == 0 && pf < n_chunks) tma_load_chunk(ring.stage[k], chunks + (size_t)pf * CHUNK_FLOATS, &ring.full[k]);
+            advance(pf, pf_pos);
+        }
+    } else {
+        if (c < n_chunks && c * 32u + lane < p.n_tri) { A = __ldg(sc.a + c * 32u + lane); B = __ldg(sc.b + c * 32u + lane); C = __ldg(sc.c + c * 32u + lane); }
+        advance(pf, pf_pos);
     }
-    for (; batch < n_batches; batch += n_warps) {
-        const uint32_t c_end = min(n_chunks, (batch + 1u) * batch_chunks);
-        for (uint32_t c = batch * batch_chunks; c < c_end; ++c) {
+    uint32_t stg = 0, phase = 0;
+    {
+        for (; c < n_chunks; advance(c, c_pos)) {
             const uint32_t t = c * 32u + lane;
+            if (TMA) {
+                mbar_wait(&ring.full[stg], phase);
+                A = reinterpret_cast<const float4*>(ring.stage[stg])[lane];
+                B = reinterpret_cast<const float4*>(ring.stage[stg] + 128)[lane];
+                C = reinterpret_cast<const float2*>(ring.stage[stg] + 256)[lane];
+            }
             const float v0 = A.x, v1 = A.y, v2 = A.z, v3 = A.w, v4 = B.x, v5 = B.y, v6 = B.z, v7 = B.w, v8 = C.x;
-            {   // prefetch the next chunk of this warp (next in the batch, or first of its next batch)
-                const uint32_t cn = (c + 1u < c_end) ? c + 1u : (batch + n_warps) * batch_chunks;
-                const uint32_t tn = cn * 32u + lane;
-                if (cn < n_chunks && tn < p.n_tri) { A = __ldg(sc.a + tn); B = __ldg(sc.b + tn); C = __ldg(sc.c + tn); }
+            if (!TMA) {   // prefetch the next chunk of this warp into registers
+                const uint32_t tn = pf * 32u + lane;
+                if (pf < n_chunks && tn < p.n_tri) { A = __ldg(sc.a + tn); B = __ldg(sc.b + tn); C = __ldg(sc.c + tn); }
+                advance(pf, pf_pos);
             }
             // ---- phase A: x'/y' transform, bounds (Triangle::mul, aabb, rasterizer.rs:58-66) --
             const float y1 = xform_row(p.m + 4, v0, v1, v2), x1 = xform_row(p.m + 0, v0, v1, v2);
@@ -187,6 +256,15 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
             // whole-frame contexts own every row; band contexts skip triangles whose destination
             // rows (y, or y+1 after a row wrap) miss the band
             const bool has_rows = t < p.n_tri && miny < maxy && (!BAND || (miny < p.row1 && maxy + 1u > p.krow0));
+            if (TMA) {
+                // every lane has consumed its nine coordinates (the transform above depends on them), so
+                // after the warp barrier no shared-memory read of this stage is outstanding: refill it
+                __syncwarp();
+                if (lane == 0 && pf < n_chunks)
+                    tma_load_chunk(ring.stage[stg], chunks + (size_t)pf * CHUNK_FLOATS, &ring.full[stg]);
+                advance(pf, pf_pos);
+                if (++stg == TMA_STAGES) { stg = 0; phase ^= 1u; }
+            }
 
             // ---- row stamps (rasterizer.rs:89-91) ----------------------------------------------
             // rowmax[y] = max(c + 1) over chunks c that stamp row y.  The lanes of a chunk are
@@ -631,6 +709,21 @@ __global__ void __launch_bounds__(256) k_zbuffer(const __grid_constant__ FramePa
         }
     }
     z[i] = out;
+}
+
+// Scene upload for the TMA feed: the three streams regrouped into 1280-byte chunks of 32 triangles.
+__global__ void __launch_bounds__(256) k_pack_chunks(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                     const float2* __restrict__ c, uint32_t n, uint32_t n_padded,
+                                                     float* __restrict__ chunks)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_padded) return;
+    float* base = chunks + (size_t)(t >> 5) * CHUNK_FLOATS;
+    const uint32_t l = t & 31u;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(base)[l] = t < n ? a[t] : z4;
+    reinterpret_cast<float4*>(base + 128)[l] = t < n ? b[t] : z4;
+    reinterpret_cast<float2*>(base + 256)[l] = t < n ? c[t] : make_float2(0.f, 0.f);
 }
 
 // Scene upload: raw soup (9 floats + 3 bytes per triangle) -> the three resident streams.
