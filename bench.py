@@ -10,7 +10,8 @@ along the reference's 64-frame turntable angle sequence (main.rs:55-58,92-96).  
 frame: update + clear + draw_mesh over the whole scene (main.rs:78-83).
 
 * value     device-timed frames/s, scene resident in HBM (uploaded once, like the reference loads
-            its meshes once), result left on the device; CUDA events on the library's stream;
+            its meshes once), results left on the device (sloth_render_device_batch: geometry of
+            frame k+1 overlaps the resolve of frame k); CUDA events on the library's stream;
             inputs (401 MB of triangles) exceed L2, so no flush is needed between steps.
 * e2e       the same frames through the public C-ABI call with HOST buffers
             (sloth_render_batch: per frame the rotation goes host->device, the cell buffer comes
@@ -216,25 +217,27 @@ def run_b200(args, rank, local_rank, world):
     frags_per_frame = float(np.mean(frags))
     ctx.stats_enable()
 
-    # ---- value: device-timed, result stays on the device ---------------------------------
-    for f in my_frames[:Wm]:
-        ctx.render_device(rots[f], d_cells.data_ptr())
+    # ---- value: device-timed, results stay on the device ----------------------------------
+    # One sloth_render_device_batch call for the K timed frames: inside it the geometry of frame k+1
+    # (issue-bound) overlaps the resolve of frame k (memory-bound) on a second stream.
+    warm_rots = np.stack([rots[f] for f in my_frames[:Wm]])
+    timed_rots = np.stack([rots[f] for f in my_frames[Wm:]])
+    ctx.render_device_batch(warm_rots, d_cells.data_ptr(), 0)
+    ctx.sync()
     barrier()
     launches0 = ctx.stats()["kernel_launches"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         t_wall0 = time.time()
         ev0.record(stream)
-        for f in my_frames[Wm:]:
-            ctx.render_device(rots[f], d_cells.data_ptr())
+        ctx.render_device_batch(timed_rots, d_cells.data_ptr(), 0)
         ev1.record(stream)
         ctx.sync()
         launches_timed = ctx.stats()["kernel_launches"] - launches0   # kernels of this library, counted at launch
         # keep the GPU in the same state a little longer so the 100 ms sampler sees the load
         t_busy = time.time()
         while time.time() - t_busy < 0.5:
-            for f in my_frames[Wm:Wm + 8]:
-                ctx.render_device(rots[f], d_cells.data_ptr())
+            ctx.render_device_batch(timed_rots[:8], d_cells.data_ptr(), 0)
             ctx.sync()
         t_wall1 = time.time()
     barrier()
@@ -299,7 +302,7 @@ def run_b200(args, rank, local_rank, world):
                          "frame_frac": (40.0 * n_tri + 4.0 * WIDTH * HEIGHT) / (dev_ms_max / K * 1e-3) / 1e9 / hbm_peak,
                          "kernel_ms": {"k_geom3": g_ms, "k_tail": float(np.mean(walk_ms)),
                                        "k_resolve": float(np.mean(resolve_ms)),
-                                       "frame": float(np.mean(frame_ms))}},
+                                       "frame_unoverlapped": float(np.mean(frame_ms))}},
             "gpu_launches": int(launches_timed),
             "clocks": clk.summary(t_wall0, t_wall1),
             "last_frame_stats": {k: last[k] for k in ("walk_tris", "walk_items", "irregular_tris", "stamp_fixups")},

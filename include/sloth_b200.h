@@ -86,6 +86,12 @@ SLOTH_API int sloth_render_batch(sloth_ctx *ctx, const float *rots, size_t n_fra
  * (same GPU) to W*H(+H) cells -- or band_rows*W cells when a band is set.
  * Runs on the context's stream; sloth_ctx_sync() waits for it. */
 SLOTH_API int sloth_render_device(sloth_ctx *ctx, const float rot[16], void *d_cells);
+/* n_frames frames with device-resident results: frame k goes to d_cells + k*frame_stride_cells
+ * (stride 0 = every frame overwrites the same buffer).  Inside the call the geometry of frame k+1
+ * overlaps the resolve of frame k on a second internal stream; when the context stream (or
+ * sloth_ctx_sync) completes, all frames are complete. */
+SLOTH_API int sloth_render_device_batch(sloth_ctx *ctx, const float *rots, size_t n_frames, void *d_cells,
+                                        size_t frame_stride_cells);
 SLOTH_API int sloth_ctx_sync(sloth_ctx *ctx);
 /* The CUDA stream (cudaStream_t) every kernel of this context is launched on, so
  * a caller can record its own events around sloth_render_device calls. */

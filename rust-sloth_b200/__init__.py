@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "sloth_render_batch", "sloth_render_device", "sloth_ctx_sync", "sloth_ctx_set_band",
     "sloth_shader_set", "sloth_stats_get", "sloth_stats_enable", "sloth_last_error",
     "sloth_rotation_from_euler", "sloth_utransform", "sloth_turntable_pitches", "sloth_cells_per_frame",
-    "sloth_pinned_alloc", "sloth_pinned_free", "sloth_ctx_stream",
+    "sloth_pinned_alloc", "sloth_pinned_free", "sloth_ctx_stream", "sloth_render_device_batch",
 ]
 
 
@@ -90,6 +90,7 @@ def load_library() -> C.CDLL:
     L.sloth_render.argtypes = [vp, fp, C.POINTER(C.c_uint32), fp]
     L.sloth_render_batch.argtypes = [vp, fp, C.c_size_t, C.POINTER(C.c_uint32)]
     L.sloth_render_device.argtypes = [vp, fp, vp]
+    L.sloth_render_device_batch.argtypes = [vp, fp, C.c_size_t, vp, C.c_size_t]
     L.sloth_ctx_sync.argtypes = [vp]
     L.sloth_ctx_stream.argtypes = [vp]
     L.sloth_ctx_stream.restype = vp
@@ -391,6 +392,13 @@ class Context:
     def render_device(self, rot: np.ndarray, device_ptr: int) -> None:
         rot = np.ascontiguousarray(rot, np.float32).reshape(16)
         _check(self._L.sloth_render_device(self._h, _fp(rot), C.c_void_p(device_ptr)))
+
+    def render_device_batch(self, rots: np.ndarray, device_ptr: int, frame_stride_cells: int = 0) -> None:
+        """Frames stay on the device (frame k at device_ptr + 4*k*frame_stride_cells); geometry of frame
+        k+1 overlaps the resolve of frame k."""
+        rots = np.ascontiguousarray(rots, np.float32).reshape(-1, 16)
+        _check(self._L.sloth_render_device_batch(self._h, _fp(rots), rots.shape[0], C.c_void_p(device_ptr),
+                                                 int(frame_stride_cells)))
 
     def stream_ptr(self) -> int:
         """cudaStream_t of this context (for torch.cuda.ExternalStream / event timing)."""

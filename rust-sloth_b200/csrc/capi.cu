@@ -86,7 +86,7 @@ struct sloth_ctx {
     uint32_t W = 0, H = 0;
     uint32_t row0 = 0, row1 = 0;  // band; row1 == 0 -> whole frame
     bool sized = false;
-    unsigned long long* keys = nullptr;
+    unsigned long long* keys[2] = {nullptr, nullptr};   // two frame-state sets (geometry k+1 overlaps resolve k)
     size_t n_key_slots = 0;       // including the halo row
     uint32_t halo_slots = 0;
     uint32_t* d_cells[2] = {nullptr, nullptr};
@@ -95,12 +95,15 @@ struct sloth_ctx {
     cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
 
     // queues + per-frame aux (rowmax and FrameAux are one allocation, cleared by one memset)
-    uint32_t* walk_tri = nullptr;
+    uint32_t* walk_tri = nullptr;      // k_geom3 -> k_tail queues: same stream, one set is enough
     unsigned long long* walk_base = nullptr;
     uint32_t* irr_tri = nullptr;
+    int last_set = 0;
+    cudaStream_t resolve_stream = nullptr;
+    cudaEvent_t ev_geom_done[2] = {nullptr, nullptr}, ev_resolved[2] = {nullptr, nullptr};
     uint32_t debug = 0;              // SLOTH_DEBUG bits, profiling experiments only
     bool scene_clean = false;        // every |coordinate| <= 2^20: no per-triangle regularity test needed
-    uint8_t* aux_region = nullptr;
+    uint8_t* aux_region[2] = {nullptr, nullptr};
     size_t aux_bytes = 0, rowmax_bytes = 0;
 
     float thr[9];
@@ -111,6 +114,8 @@ struct sloth_ctx {
     cudaEvent_t ev[EV_N] = {};
     bool ev_valid = false, ev_kernels_valid = false;
     float batch_ms_per_frame = 0.0f;
+    size_t batch_frames = 0;
+    bool batch_pending = false;      // device batch enqueued, its time not yet read
     bool last_was_batch = false;
 };
 
@@ -118,15 +123,17 @@ namespace {
 
 int free_frame_state(sloth_ctx* c)
 {
-    cudaFree(c->keys);
+    cudaFree(c->keys[0]);
+    cudaFree(c->keys[1]);
     cudaFree(c->d_cells[0]);
     cudaFree(c->d_cells[1]);
     cudaFree(c->d_z);
-    cudaFree(c->aux_region);
-    c->keys = nullptr;
+    cudaFree(c->aux_region[0]);
+    cudaFree(c->aux_region[1]);
+    c->keys[0] = c->keys[1] = nullptr;
     c->d_cells[0] = c->d_cells[1] = nullptr;
     c->d_z = nullptr;
-    c->aux_region = nullptr;
+    c->aux_region[0] = c->aux_region[1] = nullptr;
     c->sized = false;
     return 0;
 }
@@ -143,12 +150,14 @@ int alloc_frame_state(sloth_ctx* c)
     c->halo_slots = (!even && r0 > 0) ? KW : 0;
     c->n_key_slots = (size_t)rows * KW + c->halo_slots;
     c->cells_per_frame = (size_t)rows * W + ((c->image && !band) ? H : 0);
-    CU(cudaMalloc(&c->keys, std::max<size_t>(c->n_key_slots, 1) * sizeof(unsigned long long)));
-    CU(cudaMemsetAsync(c->keys, 0xFF, std::max<size_t>(c->n_key_slots, 1) * sizeof(unsigned long long), c->stream));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMalloc(&c->keys[i], std::max<size_t>(c->n_key_slots, 1) * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->keys[i], 0xFF, std::max<size_t>(c->n_key_slots, 1) * sizeof(unsigned long long), c->stream));
+    }
     for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->d_cells[i], (c->cells_per_frame + 2) * sizeof(uint32_t)));
     c->rowmax_bytes = ((((size_t)H + 31) & ~(size_t)31) + 64) * sizeof(uint32_t);
     c->aux_bytes = c->rowmax_bytes + sizeof(FrameAux);
-    CU(cudaMalloc(&c->aux_region, c->aux_bytes));
+    for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->aux_region[i], c->aux_bytes));
     c->sized = true;
     return SLOTH_OK;
 }
@@ -181,23 +190,23 @@ void build_params(const sloth_ctx* c, const float rot[16], FrameParams& p)
     p.debug = c->debug;
 }
 
-// Enqueue one frame on c->stream; the cells land in d_out (device).
-int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z, bool timed)
+Queues make_queues(const sloth_ctx* c, int set)
 {
-    FrameParams p;
-    build_params(c, rot, p);
-    Scene sc{c->sc_a, c->sc_b, c->sc_c};
     Queues q;
     q.walk_tri = c->walk_tri;
     q.walk_base = c->walk_base;
     q.irr_tri = c->irr_tri;
-    q.rowmax = reinterpret_cast<uint32_t*>(c->aux_region);
-    q.aux = reinterpret_cast<FrameAux*>(c->aux_region + c->rowmax_bytes);
-    cudaStream_t st = c->stream;
-    const bool kt = timed && (c->stat_flags & 2u);
+    q.rowmax = reinterpret_cast<uint32_t*>(c->aux_region[set]);
+    q.aux = reinterpret_cast<FrameAux*>(c->aux_region[set] + c->rowmax_bytes);
+    return q;
+}
 
-    if (timed) CU(cudaEventRecord(c->ev[EV_START], st));
-    CU(cudaMemsetAsync(c->aux_region, 0, c->aux_bytes, st));
+// Geometry half of a frame (aux clear, k_geom3, k_tail) on stream `st`, into frame-state set `set`.
+int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st, bool kt)
+{
+    Scene sc{c->sc_a, c->sc_b, c->sc_c};
+    const Queues q = make_queues(c, set);
+    CU(cudaMemsetAsync(c->aux_region[set], 0, c->aux_bytes, st));
     if (c->n_tri) {
         {
             const uint32_t n_chunks = (c->n_tri + 31) / 32;
@@ -222,42 +231,98 @@ int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z
             else kern = bounded ? (band_mode ? k_geom3<false, true, false> : k_geom3<false, false, false>)
                                 : (band_mode ? k_geom3<true, true, false> : k_geom3<true, false, false>);
             if (dyn > 16384) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            kern<<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->sc_chunks, c->keys, q, batch_chunks, rowmax_shared);
+            kern<<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->sc_chunks, c->keys[set], q, batch_chunks, rowmax_shared);
         }
         if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
-        k_tail<<<c->sm_count * 8 + c->sm_count, 128, 0, st>>>(p, sc, c->keys, q, (uint32_t)c->sm_count * 8u);
+        k_tail<<<c->sm_count * 8 + c->sm_count, 128, 0, st>>>(p, sc, c->keys[set], q, (uint32_t)c->sm_count * 8u);
         if (kt) CU(cudaEventRecord(c->ev[EV_WALK], st));
         c->launches += 2;
     } else if (kt) {
         CU(cudaEventRecord(c->ev[EV_GEOM], st));
         CU(cudaEventRecord(c->ev[EV_WALK], st));
     }
+    return SLOTH_OK;
+}
+
+// Resolve half of a frame (optional z plane, key plane -> cells, key plane reset) on stream `st`.
+int enqueue_resolve(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st, uint32_t* d_out, float* d_z)
+{
+    Scene sc{c->sc_a, c->sc_b, c->sc_c};
+    const Queues q = make_queues(c, set);
     const bool band = c->row1 != 0;
     const uint32_t rows = p.row1 - p.row0;
     const uint32_t n_tail = (c->image && !band) ? c->H : 0;
     if (d_z) {
         const uint32_t n = rows * c->W;
         // z planes are only defined for whole-frame contexts (checked by the caller)
-        k_zbuffer<<<(n + 255) / 256, 256, 0, st>>>(p, c->keys, d_z, n);
+        k_zbuffer<<<(n + 255) / 256, 256, 0, st>>>(p, c->keys[set], d_z, n);
         c->launches += 1;
     }
-    if (kt) CU(cudaEventRecord(c->ev[EV_RESOLVE_BEGIN], st));
     if ((c->W & 1u) == 0) {
         const uint32_t n_slots = rows * p.KW;
         const uint32_t n = n_slots + n_tail;
-        if (n) k_resolve_even<<<(n + 255) / 256, 256, 0, st>>>(p, sc, c->keys, q, d_out, n_slots, n_tail);
+        if (n) k_resolve_even<<<(n + 255) / 256, 256, 0, st>>>(p, sc, c->keys[set], q, d_out, n_slots, n_tail);
         c->launches += 1;
     } else {
         const uint32_t n_cells = rows * c->W;
         const uint32_t n = n_cells + n_tail;
-        if (n) k_resolve_odd<<<(n + 255) / 256, 256, 0, st>>>(p, sc, c->keys, q, d_out, n_cells, n_tail, c->halo_slots);
+        if (n) k_resolve_odd<<<(n + 255) / 256, 256, 0, st>>>(p, sc, c->keys[set], q, d_out, n_cells, n_tail, c->halo_slots);
         const uint32_t nk = (uint32_t)c->n_key_slots;
-        if (nk) k_clear_keys_odd<<<(nk + 255) / 256, 256, 0, st>>>(c->keys, nk);
+        if (nk) k_clear_keys_odd<<<(nk + 255) / 256, 256, 0, st>>>(c->keys[set], nk);
         c->launches += 2;
     }
+    return SLOTH_OK;
+}
+
+// Enqueue one frame on c->stream (frame-state set 0); the cells land in d_out (device).
+int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z, bool timed)
+{
+    FrameParams p;
+    build_params(c, rot, p);
+    cudaStream_t st = c->stream;
+    const bool kt = timed && (c->stat_flags & 2u);
+    if (timed) CU(cudaEventRecord(c->ev[EV_START], st));
+    int rc = enqueue_geometry(c, p, 0, st, kt);
+    if (rc) return rc;
+    if (kt) CU(cudaEventRecord(c->ev[EV_RESOLVE_BEGIN], st));
+    rc = enqueue_resolve(c, p, 0, st, d_out, d_z);
+    if (rc) return rc;
     if (timed) CU(cudaEventRecord(c->ev[EV_END], st));
     CU(cudaGetLastError());
     c->frames += 1;
+    c->last_set = 0;
+    return SLOTH_OK;
+}
+
+// Frames k = 0..n-1 with the geometry of frame k+1 (issue-bound, stream G = c->stream) overlapping the
+// resolve of frame k (memory-bound, stream R): two frame-state sets alternate.  Frame k's cells go to
+// out(k) on the device; before_resolve(k) / after_resolve(k) run right before / after resolve k is
+// enqueued on R (used to chain the device->host copies of the host batch).  On return everything has been enqueued and G waits for the last resolves.
+template <typename BeforeFn, typename OutFn, typename AfterFn>
+int enqueue_overlapped(sloth_ctx* c, const float* rots, size_t n_frames, BeforeFn before_resolve, OutFn out,
+                       AfterFn after_resolve)
+{
+    for (size_t k = 0; k < n_frames; ++k) {
+        const int set = (int)(k & 1);
+        FrameParams p;
+        build_params(c, rots + 16 * k, p);
+        if (k >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_resolved[set], 0));   // set's key plane and aux are free again
+        int rc = enqueue_geometry(c, p, set, c->stream, false);
+        if (rc) return rc;
+        CU(cudaEventRecord(c->ev_geom_done[set], c->stream));
+        CU(cudaStreamWaitEvent(c->resolve_stream, c->ev_geom_done[set], 0));
+        rc = before_resolve(k);
+        if (rc) return rc;
+        rc = enqueue_resolve(c, p, set, c->resolve_stream, out(k), nullptr);
+        if (rc) return rc;
+        CU(cudaEventRecord(c->ev_resolved[set], c->resolve_stream));
+        rc = after_resolve(k);
+        if (rc) return rc;
+        c->frames += 1;
+        c->last_set = set;
+    }
+    for (int set = 0; set < 2 && (size_t)set < n_frames; ++set) CU(cudaStreamWaitEvent(c->stream, c->ev_resolved[set], 0));
+    CU(cudaGetLastError());
     return SLOTH_OK;
 }
 
@@ -300,10 +365,17 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     if (const char* g = std::getenv("SLOTH_TMA")) c->tma_feed = std::atoi(g) != 0;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;   // resolve kernels squeeze in beside the persistent geometry blocks: give them priority
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->resolve_stream, cudaStreamNonBlocking, hi));
+    }
     for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) {
         CU(cudaEventCreateWithFlags(&c->ev_rendered[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_geom_done[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_resolved[i], cudaEventDisableTiming));
     }
     *out = c;
     return SLOTH_OK;
@@ -315,6 +387,7 @@ int sloth_ctx_destroy(sloth_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
+    cudaStreamSynchronize(c->resolve_stream);
     free_frame_state(c);
     cudaFree(c->sc_a);
     cudaFree(c->sc_b);
@@ -327,9 +400,12 @@ int sloth_ctx_destroy(sloth_ctx* c)
     for (int i = 0; i < 2; ++i) {
         cudaEventDestroy(c->ev_rendered[i]);
         cudaEventDestroy(c->ev_copied[i]);
+        cudaEventDestroy(c->ev_geom_done[i]);
+        cudaEventDestroy(c->ev_resolved[i]);
     }
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
+    cudaStreamDestroy(c->resolve_stream);
     delete c;
     return SLOTH_OK;
 }
@@ -341,6 +417,7 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
     if (n_tri > MAX_TRIS) return fail(SLOTH_E_TOO_LARGE, "%zu triangles; the depth key holds a 27-bit index (max %u)", n_tri, MAX_TRIS);
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->resolve_stream));
     cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_c); cudaFree(c->sc_chunks);
     c->sc_chunks = nullptr;
     cudaFree(c->walk_tri); cudaFree(c->walk_base); cudaFree(c->irr_tri);
@@ -391,6 +468,7 @@ int sloth_ctx_resize(sloth_ctx* c, uint32_t W, uint32_t H)
     if ((unsigned long long)W * H + H >= (1ull << 31)) return fail(SLOTH_E_TOO_LARGE, "W*H+H must stay below 2^31");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->resolve_stream));
     CU(cudaStreamSynchronize(c->copy_stream));
     c->W = W;
     c->H = H;
@@ -406,6 +484,7 @@ int sloth_ctx_set_band(sloth_ctx* c, uint32_t row0, uint32_t row1)
         return fail(SLOTH_E_ARG, "band [%u,%u) is not inside [0,%u)", row0, row1, c->H);
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->resolve_stream));
     CU(cudaStreamSynchronize(c->copy_stream));
     c->row0 = row0;
     c->row1 = row1;
@@ -454,6 +533,7 @@ int sloth_ctx_sync(sloth_ctx* c)
     if (!c) return fail(SLOTH_E_ARG, "null context");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->resolve_stream));
     CU(cudaStreamSynchronize(c->copy_stream));
     return SLOTH_OK;
 }
@@ -466,23 +546,53 @@ int sloth_render_batch(sloth_ctx* c, const float* rots, size_t n_frames, uint32_
     if (!rots || !cells_out) return fail(SLOTH_E_ARG, "rots/cells_out is null");
     const size_t cpf = c->cells_per_frame;
     CU(cudaEventRecord(c->ev[EV_START], c->stream));
-    for (size_t k = 0; k < n_frames; ++k) {
-        const int b = (int)(k & 1);
-        if (k >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));  // buffer b is free again
-        rc = enqueue_frame(c, rots + 16 * k, c->d_cells[b], nullptr, false);
-        if (rc) return rc;
-        CU(cudaEventRecord(c->ev_rendered[b], c->stream));
-        CU(cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[b], 0));
-        CU(cudaMemcpyAsync(cells_out + k * cpf, c->d_cells[b], cpf * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copy_stream));
-        CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
-    }
+    rc = enqueue_overlapped(
+        c, rots, n_frames,
+        [&](size_t k) -> int {   // cell buffer k&1 must have been copied out (frame k-2)
+            if (k >= 2) CU(cudaStreamWaitEvent(c->resolve_stream, c->ev_copied[k & 1], 0));
+            return SLOTH_OK;
+        },
+        [&](size_t k) { return c->d_cells[k & 1]; },
+        [&](size_t k) -> int {
+            const int b = (int)(k & 1);
+            CU(cudaStreamWaitEvent(c->copy_stream, c->ev_resolved[b], 0));
+            CU(cudaMemcpyAsync(cells_out + k * cpf, c->d_cells[b], cpf * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+            return SLOTH_OK;
+        });
+    if (rc) return rc;
     CU(cudaEventRecord(c->ev[EV_END], c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->resolve_stream));
     CU(cudaStreamSynchronize(c->copy_stream));
     float ms = 0.0f;
     CU(cudaEventElapsedTime(&ms, c->ev[EV_START], c->ev[EV_END]));
     c->batch_ms_per_frame = ms / (float)n_frames;
     c->last_was_batch = true;
+    c->ev_valid = true;
+    c->ev_kernels_valid = false;
+    return SLOTH_OK;
+}
+
+int sloth_render_device_batch(sloth_ctx* c, const float* rots, size_t n_frames, void* d_cells, size_t frame_stride_cells)
+{
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (n_frames == 0) return SLOTH_OK;
+    if (!rots || !d_cells) return fail(SLOTH_E_ARG, "rots/d_cells is null");
+    if (((uintptr_t)d_cells & 7u) != 0 || (frame_stride_cells & 1u) != 0)
+        return fail(SLOTH_E_ARG, "d_cells must be 8-byte aligned and the frame stride even");
+    uint32_t* base = static_cast<uint32_t*>(d_cells);
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    rc = enqueue_overlapped(
+        c, rots, n_frames, [&](size_t) -> int { return SLOTH_OK; },
+        [&](size_t k) { return base + k * frame_stride_cells; }, [&](size_t) -> int { return SLOTH_OK; });
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[EV_END], c->stream));   // the context stream has joined the last resolves
+    c->batch_ms_per_frame = 0.0f;
+    c->batch_frames = n_frames;
+    c->last_was_batch = true;
+    c->batch_pending = true;
     c->ev_valid = true;
     c->ev_kernels_valid = false;
     return SLOTH_OK;
@@ -514,12 +624,13 @@ int sloth_stats_get(sloth_ctx* c, sloth_stats* out)
     std::memset(out, 0, sizeof *out);
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->resolve_stream));
     out->frames = c->frames;
     out->kernel_launches = c->launches;
     out->n_tri = c->n_tri;
-    if (c->sized && c->aux_region) {
+    if (c->sized && c->aux_region[c->last_set]) {
         FrameAux aux;
-        CU(cudaMemcpy(&aux, c->aux_region + c->rowmax_bytes, sizeof aux, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&aux, c->aux_region[c->last_set] + c->rowmax_bytes, sizeof aux, cudaMemcpyDeviceToHost));
         out->fragments = aux.frag_counter;
         out->walk_tris = (uint32_t)(aux.walk_counter >> ITEM_BITS);
         out->walk_items = (uint32_t)(aux.walk_counter & ITEM_MASK);
@@ -527,6 +638,12 @@ int sloth_stats_get(sloth_ctx* c, sloth_stats* out)
         out->stamp_fixups = aux.stamp_exact;
     }
     if (c->ev_valid) {
+        if (c->last_was_batch && c->batch_pending) {
+            float ms = 0.0f;
+            CU(cudaEventElapsedTime(&ms, c->ev[EV_START], c->ev[EV_END]));
+            c->batch_ms_per_frame = ms / (float)std::max<size_t>(c->batch_frames, 1);
+            c->batch_pending = false;
+        }
         if (c->last_was_batch) out->last_frame_ms = c->batch_ms_per_frame;
         else CU(cudaEventElapsedTime(&out->last_frame_ms, c->ev[EV_START], c->ev[EV_END]));
         if (c->ev_kernels_valid && !c->last_was_batch) {

@@ -245,3 +245,27 @@ def test_tall_frame_uses_global_row_stamps():
     ocells, oz, _ = oracle.render(xyz, rgb, s0, W, H, rot, mode=1)
     cells, z, _ = gpu_frame(xyz, rgb, s0, W, H, rot)
     assert_same(cells, z, ocells, oz, "tall frame")
+
+
+def test_device_batch_overlap_equals_single_frames():
+    """sloth_render_device_batch (geometry k+1 overlapping resolve k on two streams) == frame by frame."""
+    import torch
+    xyz, rgb, s0 = meshes.icosphere(40)
+    pitches = oracle.turntable(0.0, 9)
+    rots = np.stack([oracle.rotation(0.1, p, 0.0) for p in pitches])
+    for (W, H) in [(320, 200), (161, 83)]:
+        ctx = rs.Context.blank(True)
+        ctx.set_scene(xyz, rgb, s0)
+        ctx.resize(W, H)
+        cpf = ctx.cells_per_frame()
+        stride = (cpf + 1) & ~1
+        buf = torch.zeros(len(rots) * stride, dtype=torch.int32, device="cuda")
+        ctx.render_device_batch(rots, buf.data_ptr(), stride)
+        ctx.sync()
+        got = buf.cpu().numpy().view(np.uint32).reshape(len(rots), stride)[:, :cpf]
+        for k in range(len(rots)):
+            single, _ = ctx.render(rots[k])
+            assert np.array_equal(got[k], single), f"{W}x{H} frame {k}"
+            ocells, _, _ = oracle.render(xyz, rgb, s0, W, H, rots[k], mode=1)
+            assert np.array_equal(single, ocells)
+        ctx.close()
