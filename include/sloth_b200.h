@@ -82,12 +82,13 @@ SLOTH_API int sloth_render(sloth_ctx *ctx, const float rot[16], uint32_t *cells_
  * device->host copies are pipelined across frames. */
 SLOTH_API int sloth_render_batch(sloth_ctx *ctx, const float *rots, size_t n_frames, uint32_t *cells_out);
 
-/* Same frame, but the result stays on the device: d_cells is a device pointer
+/* Same frame, but the result stays on the device: d_cells is a 16-byte aligned device pointer
  * (same GPU) to W*H(+H) cells -- or band_rows*W cells when a band is set.
  * Runs on the context's stream; sloth_ctx_sync() waits for it. */
 SLOTH_API int sloth_render_device(sloth_ctx *ctx, const float rot[16], void *d_cells);
 /* n_frames frames with device-resident results: frame k goes to d_cells + k*frame_stride_cells
- * (stride 0 = every frame overwrites the same buffer).  Inside the call the geometry of frame k+1
+
+ * (a multiple of 4 cells; stride 0 = every frame overwrites the same buffer).  Inside the call the geometry of frame k+1
  * overlaps the resolve of frame k on a second internal stream; when the context stream (or
  * sloth_ctx_sync) completes, all frames are complete. */
 SLOTH_API int sloth_render_device_batch(sloth_ctx *ctx, const float *rots, size_t n_frames, void *d_cells,

@@ -75,7 +75,8 @@ struct sloth_ctx {
     // scene
     float4* sc_a = nullptr;
     float4* sc_b = nullptr;
-    float2* sc_c = nullptr;
+    float* sc_z3 = nullptr;
+    uint32_t* sc_rgb = nullptr;
     float* sc_chunks = nullptr;      // TMA feed: 1280-byte chunks of 32 triangles
     bool tma_feed = false;           // SLOTH_TMA=1 feeds k_geom3 through cp.async.bulk + mbarrier (measured 3 % slower)
     uint32_t n_tri = 0;
@@ -204,7 +205,7 @@ Queues make_queues(const sloth_ctx* c, int set)
 // Geometry half of a frame (aux clear, k_geom3, k_tail) on stream `st`, into frame-state set `set`.
 int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st, bool kt)
 {
-    Scene sc{c->sc_a, c->sc_b, c->sc_c};
+    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb};
     const Queues q = make_queues(c, set);
     CU(cudaMemsetAsync(c->aux_region[set], 0, c->aux_bytes, st));
     if (c->n_tri) {
@@ -247,7 +248,7 @@ int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t s
 // Resolve half of a frame (optional z plane, key plane -> cells, key plane reset) on stream `st`.
 int enqueue_resolve(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st, uint32_t* d_out, float* d_z)
 {
-    Scene sc{c->sc_a, c->sc_b, c->sc_c};
+    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb};
     const Queues q = make_queues(c, set);
     const bool band = c->row1 != 0;
     const uint32_t rows = p.row1 - p.row0;
@@ -391,7 +392,8 @@ int sloth_ctx_destroy(sloth_ctx* c)
     free_frame_state(c);
     cudaFree(c->sc_a);
     cudaFree(c->sc_b);
-    cudaFree(c->sc_c);
+    cudaFree(c->sc_z3);
+    cudaFree(c->sc_rgb);
     cudaFree(c->sc_chunks);
     cudaFree(c->walk_tri);
     cudaFree(c->walk_base);
@@ -418,16 +420,17 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->resolve_stream));
-    cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_c); cudaFree(c->sc_chunks);
+    cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_z3); cudaFree(c->sc_rgb); cudaFree(c->sc_chunks);
     c->sc_chunks = nullptr;
     cudaFree(c->walk_tri); cudaFree(c->walk_base); cudaFree(c->irr_tri);
-    c->sc_a = c->sc_b = nullptr; c->sc_c = nullptr;
+    c->sc_a = c->sc_b = nullptr; c->sc_z3 = nullptr; c->sc_rgb = nullptr;
     c->walk_tri = c->irr_tri = nullptr; c->walk_base = nullptr;
     c->have_scene = false;
     const size_t n = n_tri ? n_tri : 1;
     CU(cudaMalloc(&c->sc_a, n * sizeof(float4)));
     CU(cudaMalloc(&c->sc_b, n * sizeof(float4)));
-    CU(cudaMalloc(&c->sc_c, n * sizeof(float2)));
+    CU(cudaMalloc(&c->sc_z3, n * sizeof(float)));
+    CU(cudaMalloc(&c->sc_rgb, n * sizeof(uint32_t)));
     const size_t n_padded = (n + 31) & ~(size_t)31;
     CU(cudaMalloc(&c->sc_chunks, n_padded / 32 * CHUNK_BYTES));
     CU(cudaMalloc(&c->walk_tri, n * sizeof(uint32_t)));
@@ -440,8 +443,8 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
         CU(cudaMalloc(&d_rgb, n_tri * 3));
         CU(cudaMemcpyAsync(d_xyz, xyz, n_tri * 9 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(d_rgb, rgb, n_tri * 3, cudaMemcpyHostToDevice, c->stream));
-        k_pack_scene<<<(unsigned)((n_tri + 255) / 256), 256, 0, c->stream>>>(d_xyz, d_rgb, (uint32_t)n_tri, c->sc_a, c->sc_b, c->sc_c);
-        k_pack_chunks<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(c->sc_a, c->sc_b, c->sc_c, (uint32_t)n_tri, (uint32_t)n_padded, c->sc_chunks);
+        k_pack_scene<<<(unsigned)((n_tri + 255) / 256), 256, 0, c->stream>>>(d_xyz, d_rgb, (uint32_t)n_tri, c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb);
+        k_pack_chunks<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(c->sc_a, c->sc_b, c->sc_z3, (uint32_t)n_tri, (uint32_t)n_padded, c->sc_chunks);
         c->launches += 2;
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(c->stream));
@@ -517,7 +520,7 @@ int sloth_render_device(sloth_ctx* c, const float rot[16], void* d_cells)
     int rc = check_ready(c);
     if (rc) return rc;
     if (!rot || !d_cells) return fail(SLOTH_E_ARG, "rot/d_cells is null");
-    if (((uintptr_t)d_cells & 7u) != 0) return fail(SLOTH_E_ARG, "d_cells must be 8-byte aligned");
+    if (((uintptr_t)d_cells & 15u) != 0) return fail(SLOTH_E_ARG, "d_cells must be 16-byte aligned");
     rc = enqueue_frame(c, rot, static_cast<uint32_t*>(d_cells), nullptr, true);
     if (rc) return rc;
     c->ev_valid = true;
@@ -580,8 +583,8 @@ int sloth_render_device_batch(sloth_ctx* c, const float* rots, size_t n_frames, 
     if (rc) return rc;
     if (n_frames == 0) return SLOTH_OK;
     if (!rots || !d_cells) return fail(SLOTH_E_ARG, "rots/d_cells is null");
-    if (((uintptr_t)d_cells & 7u) != 0 || (frame_stride_cells & 1u) != 0)
-        return fail(SLOTH_E_ARG, "d_cells must be 8-byte aligned and the frame stride even");
+    if (((uintptr_t)d_cells & 15u) != 0 || (frame_stride_cells & 3u) != 0)
+        return fail(SLOTH_E_ARG, "d_cells must be 16-byte aligned and the frame stride a multiple of 4 cells");
     uint32_t* base = static_cast<uint32_t*>(d_cells);
     CU(cudaEventRecord(c->ev[EV_START], c->stream));
     rc = enqueue_overlapped(

@@ -37,14 +37,14 @@ struct Queues {
 };
 
 // ---------------------------------------------------------------------------------
-// TMA feed for k_geom3: the scene is also kept as 1280-byte chunks of 32 triangles
-// ([32 x float4 A][32 x float4 B][32 x float2 C], same fields as Scene), so one elected
+// TMA feed for k_geom3: the geometry streams are also kept as 1152-byte chunks of 32 triangles
+// ([32 x float4 A][32 x float4 B][32 x float v3.z], same fields as Scene), so one elected
 // lane moves a whole chunk with a single cp.async.bulk into a per-warp 3-stage ring and the
 // warp waits on the stage's mbarrier: no per-lane address arithmetic or predicates, no
 // registers held by loads in flight, two chunks of look-ahead.
 // ---------------------------------------------------------------------------------
-static constexpr uint32_t CHUNK_FLOATS = 320;               // 128 + 128 + 64
-static constexpr uint32_t CHUNK_BYTES = CHUNK_FLOATS * 4;   // 1280
+static constexpr uint32_t CHUNK_FLOATS = 288;               // 128 + 128 + 32
+static constexpr uint32_t CHUNK_BYTES = CHUNK_FLOATS * 4;   // 1152
 static constexpr uint32_t TMA_STAGES = 3;
 
 SLOTH_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -217,14 +217,14 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
     };
     TmaRing& ring = rings[TMA ? warp : 0];
     float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
-    float2 C = make_float2(0.f, 0.f);
+    float C = 0.f;
     if (TMA) {
         for (uint32_t k = 0; k < TMA_STAGES; ++k) {
             if (lane == 0 && pf < n_chunks) tma_load_chunk(ring.stage[k], chunks + (size_t)pf * CHUNK_FLOATS, &ring.full[k]);
             advance(pf, pf_pos);
         }
     } else {
-        if (c < n_chunks && c * 32u + lane < p.n_tri) { A = __ldg(sc.a + c * 32u + lane); B = __ldg(sc.b + c * 32u + lane); C = __ldg(sc.c + c * 32u + lane); }
+        if (c < n_chunks && c * 32u + lane < p.n_tri) { A = __ldg(sc.a + c * 32u + lane); B = __ldg(sc.b + c * 32u + lane); C = __ldg(sc.z3 + c * 32u + lane); }
         advance(pf, pf_pos);
     }
     uint32_t stg = 0, phase = 0;
@@ -235,12 +235,12 @@ __global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constan
                 mbar_wait(&ring.full[stg], phase);
                 A = reinterpret_cast<const float4*>(ring.stage[stg])[lane];
                 B = reinterpret_cast<const float4*>(ring.stage[stg] + 128)[lane];
-                C = reinterpret_cast<const float2*>(ring.stage[stg] + 256)[lane];
+                C = ring.stage[stg][256 + lane];
             }
-            const float v0 = A.x, v1 = A.y, v2 = A.z, v3 = A.w, v4 = B.x, v5 = B.y, v6 = B.z, v7 = B.w, v8 = C.x;
+            const float v0 = A.x, v1 = A.y, v2 = A.z, v3 = A.w, v4 = B.x, v5 = B.y, v6 = B.z, v7 = B.w, v8 = C;
             if (!TMA) {   // prefetch the next chunk of this warp into registers
                 const uint32_t tn = pf * 32u + lane;
-                if (pf < n_chunks && tn < p.n_tri) { A = __ldg(sc.a + tn); B = __ldg(sc.b + tn); C = __ldg(sc.c + tn); }
+                if (pf < n_chunks && tn < p.n_tri) { A = __ldg(sc.a + tn); B = __ldg(sc.b + tn); C = __ldg(sc.z3 + tn); }
                 advance(pf, pf_pos);
             }
             // ---- phase A: x'/y' transform, bounds (Triangle::mul, aabb, rasterizer.rs:58-66) --
@@ -471,8 +471,7 @@ SLOTH_DEV void walk_body(const FrameParams& p, const Scene& sc, unsigned long lo
         const uint32_t t = q.walk_tri[lo];
         const uint32_t band = (uint32_t)(item - q.walk_base[lo]);
         float v[9];
-        uint32_t rgb;
-        load_tri(sc, t, v, rgb);
+        load_tri(sc, t, v);
         Setup s;
         setup_tri(p, v, s);
         Shade sh;
@@ -524,8 +523,7 @@ SLOTH_DEV void irregular_body(const FrameParams& p, const Scene& sc, unsigned lo
     for (uint32_t i = block; i < n; i += n_blocks) {
         const uint32_t t = q.irr_tri[i];
         float v[9];
-        uint32_t rgb;
-        load_tri(sc, t, v, rgb);
+        load_tri(sc, t, v);
         Setup s;
         setup_tri(p, v, s);
         Shade sh;
@@ -563,7 +561,7 @@ SLOTH_DEV uint32_t key_tri(unsigned long long k) { return ((uint32_t)k >> 5) & M
 SLOTH_DEV uint32_t cell_of(const FrameParams& p, const Scene& sc, unsigned long long key)
 {
     const uint32_t g = (uint32_t)key & 15u;
-    const uint32_t rgb = __float_as_uint(__ldg(&sc.c[key_tri(key)].y));
+    const uint32_t rgb = __ldg(sc.rgb + key_tri(key));
     return (uint32_t)(uint8_t)p.glyph[g] | (rgb << 8);
 }
 
@@ -590,8 +588,7 @@ SLOTH_DEV bool stamp_beats_fragment(const FrameParams& p, const Scene& sc, const
         bool hit = false;
         if (t >= tw && t < p.n_tri) {
             float v[9];
-            uint32_t rgb;
-            load_tri(sc, t, v, rgb);
+            load_tri(sc, t, v);
             Setup s;
             setup_tri(p, v, s);
             hit = r >= s.miny && r < s.maxy;
@@ -605,7 +602,9 @@ SLOTH_DEV bool stamp_beats_fragment(const FrameParams& p, const Scene& sc, const
     return newline;
 }
 
-// W even: ids are even, one key slot owns cells (2k, 2k+1) of its row.
+// W even: ids are even, one key slot owns cells (2k, 2k+1) of its row.  One slot per thread
+// (two slots per thread with 16-byte accesses measured 3x slower: half the warps, same
+// dependent load -> gather chain, so less latency hiding).
 __global__ void __launch_bounds__(256) k_resolve_even(const __grid_constant__ FrameParams p, const Scene sc,
                                                       unsigned long long* __restrict__ keys, const Queues q,
                                                       uint32_t* __restrict__ cells, uint32_t n_slots,
@@ -711,9 +710,9 @@ __global__ void __launch_bounds__(256) k_zbuffer(const __grid_constant__ FramePa
     z[i] = out;
 }
 
-// Scene upload for the TMA feed: the three streams regrouped into 1280-byte chunks of 32 triangles.
+// Scene upload for the TMA feed: the geometry streams regrouped into 1152-byte chunks of 32 triangles.
 __global__ void __launch_bounds__(256) k_pack_chunks(const float4* __restrict__ a, const float4* __restrict__ b,
-                                                     const float2* __restrict__ c, uint32_t n, uint32_t n_padded,
+                                                     const float* __restrict__ z3, uint32_t n, uint32_t n_padded,
                                                      float* __restrict__ chunks)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -723,22 +722,21 @@ __global__ void __launch_bounds__(256) k_pack_chunks(const float4* __restrict__ 
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     reinterpret_cast<float4*>(base)[l] = t < n ? a[t] : z4;
     reinterpret_cast<float4*>(base + 128)[l] = t < n ? b[t] : z4;
-    reinterpret_cast<float2*>(base + 256)[l] = t < n ? c[t] : make_float2(0.f, 0.f);
+    base[256 + l] = t < n ? z3[t] : 0.f;
 }
 
-// Scene upload: raw soup (9 floats + 3 bytes per triangle) -> the three resident streams.
+// Scene upload: raw soup (9 floats + 3 bytes per triangle) -> the four resident streams.
 __global__ void __launch_bounds__(256) k_pack_scene(const float* __restrict__ xyz, const uint8_t* __restrict__ rgb,
                                                     uint32_t n, float4* __restrict__ a, float4* __restrict__ b,
-                                                    float2* __restrict__ c)
+                                                    float* __restrict__ z3, uint32_t* __restrict__ col)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const float* v = xyz + (size_t)t * 9;
     a[t] = make_float4(v[0], v[1], v[2], v[3]);
     b[t] = make_float4(v[4], v[5], v[6], v[7]);
-    const uint32_t col = (uint32_t)rgb[(size_t)t * 3] | ((uint32_t)rgb[(size_t)t * 3 + 1] << 8) |
-                         ((uint32_t)rgb[(size_t)t * 3 + 2] << 16);
-    c[t] = make_float2(v[8], __uint_as_float(col));
+    z3[t] = v[8];
+    col[t] = (uint32_t)rgb[(size_t)t * 3] | ((uint32_t)rgb[(size_t)t * 3 + 1] << 8) | ((uint32_t)rgb[(size_t)t * 3 + 2] << 16);
 }
 
 }  // namespace sloth

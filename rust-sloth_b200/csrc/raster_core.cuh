@@ -40,11 +40,13 @@ struct FrameParams {
     char glyph[12];    // 10 glyphs (+pad)
 };
 
-// Resident scene: 40 B per triangle in three coalesced streams.
+// Resident scene: 40 B per triangle in four coalesced streams; the geometry kernels read the first
+// three (36 B), only resolve reads the colours.
 struct Scene {
-    const float4* __restrict__ a;  // v1.x v1.y v1.z v2.x
-    const float4* __restrict__ b;  // v2.y v2.z v3.x v3.y
-    const float2* __restrict__ c;  // v3.z, rgb bits (r | g<<8 | b<<16)
+    const float4* __restrict__ a;     // v1.x v1.y v1.z v2.x
+    const float4* __restrict__ b;     // v2.y v2.z v3.x v3.y
+    const float* __restrict__ z3;     // v3.z
+    const uint32_t* __restrict__ rgb; // r | g<<8 | b<<16
 };
 
 // Transformed triangle + everything hoistable out of the per-candidate loop.
@@ -66,15 +68,14 @@ SLOTH_DEV float xform_row(const float* r, float x, float y, float z)
     return add(add(add(mul(r[0], x), mul(r[1], y)), mul(r[2], z)), r[3]);
 }
 
-SLOTH_DEV void load_tri(const Scene& sc, uint32_t t, float (&v)[9], uint32_t& rgb)
+SLOTH_DEV void load_tri(const Scene& sc, uint32_t t, float (&v)[9])
 {
     const float4 A = __ldg(sc.a + t);
     const float4 B = __ldg(sc.b + t);
-    const float2 C = __ldg(sc.c + t);
+    const float C = __ldg(sc.z3 + t);
     v[0] = A.x; v[1] = A.y; v[2] = A.z;
     v[3] = A.w; v[4] = B.x; v[5] = B.y;
-    v[6] = B.z; v[7] = B.w; v[8] = C.x;
-    rgb = __float_as_uint(C.y);
+    v[6] = B.z; v[7] = B.w; v[8] = C;
 }
 
 SLOTH_DEV bool in_limit(float v) { return fabsf(v) <= REGULAR_LIMIT; }  // false for NaN

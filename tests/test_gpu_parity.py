@@ -258,7 +258,7 @@ def test_device_batch_overlap_equals_single_frames():
         ctx.set_scene(xyz, rgb, s0)
         ctx.resize(W, H)
         cpf = ctx.cells_per_frame()
-        stride = (cpf + 1) & ~1
+        stride = (cpf + 3) & ~3
         buf = torch.zeros(len(rots) * stride, dtype=torch.int32, device="cuda")
         ctx.render_device_batch(rots, buf.data_ptr(), stride)
         ctx.sync()
