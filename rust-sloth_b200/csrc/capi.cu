@@ -78,6 +78,7 @@ struct sloth_ctx {
     float* sc_z3 = nullptr;
     uint32_t* sc_rgb = nullptr;
     float* sc_chunks = nullptr;      // TMA feed: 1280-byte chunks of 32 triangles
+    uint32_t geom_blocks_per_sm = G3_BLOCKS_PER_SM;   // SLOTH_GRID overrides (profiling)
     bool tma_feed = false;           // SLOTH_TMA=1 feeds k_geom3 through cp.async.bulk + mbarrier (measured 3 % slower)
     uint32_t n_tri = 0;
     float scene_max = 0.0f;
@@ -213,10 +214,11 @@ int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t s
             const uint32_t n_chunks = (c->n_tri + 31) / 32;
             // consecutive chunks per warp turn: 16 for big scenes (neighbouring triangles share rows and
             // cache lines), fewer when that would leave warps without work
-            const uint32_t warps_avail = (uint32_t)c->sm_count * 3u * G3_WARPS;
+            const uint32_t blocks_per_sm = c->geom_blocks_per_sm;
+            const uint32_t warps_avail = (uint32_t)c->sm_count * blocks_per_sm * G3_WARPS;
             const uint32_t batch_chunks = std::max<uint32_t>(1u, std::min<uint32_t>(G3_BATCH_MAX, n_chunks / (warps_avail * 4u)));
             const uint32_t n_batches = (n_chunks + batch_chunks - 1) / batch_chunks;
-            const uint32_t grid = std::min<uint32_t>((n_batches + G3_WARPS - 1) / G3_WARPS, (uint32_t)c->sm_count * 3u);
+            const uint32_t grid = std::min<uint32_t>((n_batches + G3_WARPS - 1) / G3_WARPS, (uint32_t)c->sm_count * blocks_per_sm);
             // a clean scene under a bounded matrix cannot produce |x'|,|y'| > 2^40: skip the per-triangle test
             bool bounded = c->scene_clean;
             for (int i = 0; i < 8; ++i) bounded = bounded && std::fabs(p.m[i]) <= 131072.0f;
@@ -364,6 +366,7 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     c->sm_count = prop.multiProcessorCount;
     if (const char* g = std::getenv("SLOTH_DEBUG")) c->debug = (uint32_t)std::atoi(g);
     if (const char* g = std::getenv("SLOTH_TMA")) c->tma_feed = std::atoi(g) != 0;
+    if (const char* g = std::getenv("SLOTH_GRID")) c->geom_blocks_per_sm = (uint32_t)std::max(1, std::atoi(g));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     {

@@ -103,6 +103,9 @@ struct TmaRing {
 //      one edge evaluation, depth, glyph and a 64-bit atomicMin into the key plane.
 // ---------------------------------------------------------------------------------
 static constexpr uint32_t G3_WARPS = 8;          // warps per block
+#ifndef G3_BLOCKS_PER_SM
+#define G3_BLOCKS_PER_SM 3
+#endif
 static constexpr uint32_t G3_BATCH_MAX = 16;     // consecutive chunks per warp turn (fewer for small scenes)
 static constexpr uint32_t G3_RING = 64;          // per-warp ring of covering triangles (power of two)
 
@@ -178,7 +181,7 @@ SLOTH_DEV void g3_emit(const FrameParams& p, const G3Queue& wq, uint32_t head, u
 }
 
 template <bool CHECK_REGULAR, bool BAND, bool TMA>
-__global__ void __launch_bounds__(G3_WARPS * 32, 3) k_geom3(const __grid_constant__ FrameParams p, const Scene sc,
+__global__ void __launch_bounds__(G3_WARPS * 32, G3_BLOCKS_PER_SM) k_geom3(const __grid_constant__ FrameParams p, const Scene sc,
                                                             const float* __restrict__ chunks,
                                                             unsigned long long* __restrict__ keys, const Queues q,
                                                             const uint32_t batch_chunks, const uint32_t rowmax_shared)
