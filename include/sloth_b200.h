@@ -108,6 +108,26 @@ SLOTH_API void *sloth_ctx_stream(sloth_ctx *ctx);
  */
 SLOTH_API int sloth_ctx_set_band(sloth_ctx *ctx, uint32_t row0, uint32_t row1);
 
+/*
+ * Context::flush on the device (src/context.rs:50-92).  The exact bytes the
+ * reference prints for the cell buffer, produced on the GPU:
+ *   mode 0  plain glyphs                                  flush(color = false)   (without println's '\n')
+ *   mode 1  ESC[48;2;25;25;25m ESC[38;2;R;G;Bm c ESC[0m   flush(true, false)     (crossterm 0.18)
+ *   mode 2  <span style="color:rgb(R,G,B)">c              flush(true, true)      (the -j export)
+ * Frame prefixes/suffixes (cursor move, "`\n", "`,\n" ...) stay with the host.
+ * sloth_text_capacity: worst-case bytes of one frame.  sloth_render_text(_batch): render + flush,
+ * text of frame k at text_out + k*frame_stride (>= capacity), its length in lens_out[k]; rendering,
+ * serialisation and device->host copies of consecutive frames are pipelined.
+ */
+SLOTH_API size_t sloth_text_capacity(const sloth_ctx *ctx, int mode);
+SLOTH_API int sloth_render_text(sloth_ctx *ctx, const float rot[16], int mode, char *text_out, size_t cap,
+                                size_t *len_out);
+SLOTH_API int sloth_render_text_batch(sloth_ctx *ctx, const float *rots, size_t n_frames, int mode, char *text_out,
+                                      size_t frame_stride, size_t *lens_out);
+/* Serialise a cell buffer that is already on the device (same GPU); returns the text length. */
+SLOTH_API int sloth_flush_device(sloth_ctx *ctx, int mode, const void *d_cells, size_t n_cells, void *d_text,
+                                 size_t cap, size_t *len_out);
+
 /* The `shader: F` closure of draw_mesh (rasterizer.rs:39-41), restricted to
  * what the reference ever passes: 9 ascending `<=` thresholds and 10 glyphs
  * (the last one for "above all thresholds or NaN").  Default = default_shader,

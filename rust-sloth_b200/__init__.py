@@ -47,6 +47,7 @@ ABI_SYMBOLS = [
     "sloth_shader_set", "sloth_stats_get", "sloth_stats_enable", "sloth_last_error",
     "sloth_rotation_from_euler", "sloth_utransform", "sloth_turntable_pitches", "sloth_cells_per_frame",
     "sloth_pinned_alloc", "sloth_pinned_free", "sloth_ctx_stream", "sloth_render_device_batch",
+    "sloth_text_capacity", "sloth_render_text", "sloth_render_text_batch", "sloth_flush_device",
 ]
 
 
@@ -91,6 +92,11 @@ def load_library() -> C.CDLL:
     L.sloth_render_batch.argtypes = [vp, fp, C.c_size_t, C.POINTER(C.c_uint32)]
     L.sloth_render_device.argtypes = [vp, fp, vp]
     L.sloth_render_device_batch.argtypes = [vp, fp, C.c_size_t, vp, C.c_size_t]
+    L.sloth_text_capacity.argtypes = [vp, C.c_int]
+    L.sloth_text_capacity.restype = C.c_size_t
+    L.sloth_render_text.argtypes = [vp, fp, C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.sloth_render_text_batch.argtypes = [vp, fp, C.c_size_t, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.sloth_flush_device.argtypes = [vp, C.c_int, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.sloth_ctx_sync.argtypes = [vp]
     L.sloth_ctx_stream.argtypes = [vp]
     L.sloth_ctx_stream.restype = vp
@@ -399,6 +405,22 @@ class Context:
         rots = np.ascontiguousarray(rots, np.float32).reshape(-1, 16)
         _check(self._L.sloth_render_device_batch(self._h, _fp(rots), rots.shape[0], C.c_void_p(device_ptr),
                                                  int(frame_stride_cells)))
+
+    def render_text_batch(self, rots: np.ndarray, mode: int) -> list[bytes]:
+        """Render + device-side Context::flush: the exact cell byte stream of every frame
+        (mode 0 plain, 1 ANSI, 2 webify <span>s)."""
+        rots = np.ascontiguousarray(rots, np.float32).reshape(-1, 16)
+        n = rots.shape[0]
+        cap = int(self._L.sloth_text_capacity(self._h, mode))
+        stride = (cap + 63) & ~63
+        buf = PinnedBuffer((n * stride + 3) // 4)
+        lens = (C.c_size_t * n)()
+        try:
+            _check(self._L.sloth_render_text_batch(self._h, _fp(rots), n, mode, C.c_void_p(buf.array.ctypes.data), stride, lens))
+            raw = buf.array.view(np.uint8)
+            return [bytes(raw[k * stride:k * stride + lens[k]]) for k in range(n)]
+        finally:
+            buf.free()
 
     def stream_ptr(self) -> int:
         """cudaStream_t of this context (for torch.cuda.ExternalStream / event timing)."""

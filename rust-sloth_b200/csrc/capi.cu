@@ -19,6 +19,7 @@
 
 #include "../../include/sloth_b200.h"
 #include "kernels.cuh"
+#include "flush.cuh"
 
 using namespace sloth;
 
@@ -110,6 +111,15 @@ struct sloth_ctx {
 
     float thr[9];
     char glyph[10];
+
+    // device-side flush (text serialisation)
+    char* d_text[2] = {nullptr, nullptr};
+    size_t d_text_cap = 0;
+    uint32_t* flush_block_sum = nullptr;
+    unsigned long long* flush_block_off = nullptr;
+    unsigned long long* d_text_total = nullptr;      // [2]
+    unsigned long long* h_text_total = nullptr;      // [2], pinned
+    cudaEvent_t ev_text[2] = {nullptr, nullptr};
 
     uint32_t stat_flags = 0;
     uint64_t frames = 0, launches = 0;
@@ -329,6 +339,48 @@ int enqueue_overlapped(sloth_ctx* c, const float* rots, size_t n_frames, BeforeF
     return SLOTH_OK;
 }
 
+size_t text_bytes_per_cell(int mode) { return mode == 0 ? 1 : (mode == 1 ? 40 : 38); }
+
+int ensure_text_buffers(sloth_ctx* c, int mode)
+{
+    const size_t need = c->cells_per_frame * text_bytes_per_cell(mode) + 64;
+    if (!c->h_text_total) {
+        CU(cudaHostAlloc(&c->h_text_total, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+        CU(cudaMalloc(&c->d_text_total, 2 * sizeof(unsigned long long)));
+        for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&c->ev_text[i], cudaEventDisableTiming));
+    }
+    if (need > c->d_text_cap) {
+        CU(cudaStreamSynchronize(c->resolve_stream));
+        CU(cudaStreamSynchronize(c->copy_stream));
+        for (int i = 0; i < 2; ++i) { cudaFree(c->d_text[i]); c->d_text[i] = nullptr; }
+        cudaFree(c->flush_block_sum); cudaFree(c->flush_block_off);
+        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->d_text[i], need));
+        const size_t nb = (c->cells_per_frame + FLUSH_CELLS_PER_BLOCK - 1) / FLUSH_CELLS_PER_BLOCK + 1;
+        CU(cudaMalloc(&c->flush_block_sum, nb * sizeof(uint32_t)));
+        CU(cudaMalloc(&c->flush_block_off, nb * sizeof(unsigned long long)));
+        c->d_text_cap = need;
+    }
+    return SLOTH_OK;
+}
+
+// Context::flush on the device: d_cells (n_cells) -> d_text, total length to d_total (all on `st`).
+int enqueue_flush(sloth_ctx* c, int mode, const uint32_t* d_cells, size_t n_cells, char* d_text,
+                  unsigned long long* d_total, uint32_t* block_sum, unsigned long long* block_off, cudaStream_t st)
+{
+    const uint32_t nb = (uint32_t)((n_cells + FLUSH_CELLS_PER_BLOCK - 1) / FLUSH_CELLS_PER_BLOCK);
+    if (nb == 0) {
+        CU(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
+        return SLOTH_OK;
+    }
+    const size_t smem = FLUSH_CELLS_PER_BLOCK * text_bytes_per_cell(mode) + 16;
+    k_flush_sizes<<<nb, FLUSH_THREADS, 0, st>>>(d_cells, (uint32_t)n_cells, mode, block_sum);
+    k_flush_scan<<<1, 1024, 0, st>>>(block_sum, nb, block_off, d_total);
+    k_flush_write<<<nb, FLUSH_THREADS, smem, st>>>(d_cells, (uint32_t)n_cells, mode, block_off, d_text);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    return SLOTH_OK;
+}
+
 int check_ready(sloth_ctx* c)
 {
     if (!c) return fail(SLOTH_E_ARG, "null context");
@@ -393,6 +445,9 @@ int sloth_ctx_destroy(sloth_ctx* c)
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamSynchronize(c->resolve_stream);
     free_frame_state(c);
+    for (int i = 0; i < 2; ++i) { cudaFree(c->d_text[i]); if (c->ev_text[i]) cudaEventDestroy(c->ev_text[i]); }
+    cudaFree(c->flush_block_sum); cudaFree(c->flush_block_off); cudaFree(c->d_text_total);
+    if (c->h_text_total) cudaFreeHost(c->h_text_total);
     cudaFree(c->sc_a);
     cudaFree(c->sc_b);
     cudaFree(c->sc_z3);
@@ -602,6 +657,93 @@ int sloth_render_device_batch(sloth_ctx* c, const float* rots, size_t n_frames, 
     c->ev_valid = true;
     c->ev_kernels_valid = false;
     return SLOTH_OK;
+}
+
+size_t sloth_text_capacity(const sloth_ctx* c, int mode)
+{
+    if (!c || mode < 0 || mode > 2) return 0;
+    return c->cells_per_frame * text_bytes_per_cell(mode);
+}
+
+int sloth_flush_device(sloth_ctx* c, int mode, const void* d_cells, size_t n_cells, void* d_text, size_t cap, size_t* len_out)
+{
+    if (!c || !d_cells || !d_text || !len_out) return fail(SLOTH_E_ARG, "null argument");
+    if (mode < 0 || mode > 2) return fail(SLOTH_E_ARG, "mode must be 0 (plain), 1 (ANSI) or 2 (webify)");
+    if (cap < n_cells * text_bytes_per_cell(mode)) return fail(SLOTH_E_ARG, "text buffer smaller than the worst case (%zu bytes)", n_cells * text_bytes_per_cell(mode));
+    CU(cudaSetDevice(c->device));
+    uint32_t* bs = nullptr;
+    unsigned long long* bo = nullptr;
+    unsigned long long* tot = nullptr;
+    const size_t nb = (n_cells + FLUSH_CELLS_PER_BLOCK - 1) / FLUSH_CELLS_PER_BLOCK + 1;
+    CU(cudaMalloc(&bs, nb * sizeof(uint32_t)));
+    CU(cudaMalloc(&bo, nb * sizeof(unsigned long long)));
+    CU(cudaMalloc(&tot, sizeof(unsigned long long)));
+    int rc = enqueue_flush(c, mode, static_cast<const uint32_t*>(d_cells), n_cells, static_cast<char*>(d_text), tot, bs, bo, c->stream);
+    unsigned long long h = 0;
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(&h, tot, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(SLOTH_E_CUDA, "flush failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(bs); cudaFree(bo); cudaFree(tot);
+    *len_out = (size_t)h;
+    return rc;
+}
+
+int sloth_render_text_batch(sloth_ctx* c, const float* rots, size_t n_frames, int mode, char* text_out, size_t frame_stride,
+                            size_t* lens_out)
+{
+    int rc = check_ready(c);
+    if (rc) return rc;
+    if (n_frames == 0) return SLOTH_OK;
+    if (!rots || !text_out || !lens_out) return fail(SLOTH_E_ARG, "null argument");
+    if (mode < 0 || mode > 2) return fail(SLOTH_E_ARG, "mode must be 0 (plain), 1 (ANSI) or 2 (webify)");
+    if (frame_stride < sloth_text_capacity(c, mode)) return fail(SLOTH_E_ARG, "frame_stride below sloth_text_capacity()");
+    rc = ensure_text_buffers(c, mode);
+    if (rc) return rc;
+    const size_t cpf = c->cells_per_frame;
+    // frame j's text is complete on the device once ev_text[j&1] fires: read its length, start its copy
+    auto finish = [&](size_t j) -> int {
+        const int b = (int)(j & 1);
+        CU(cudaEventSynchronize(c->ev_text[b]));
+        const size_t len = (size_t)c->h_text_total[b];
+        lens_out[j] = len;
+        CU(cudaMemcpyAsync(text_out + j * frame_stride, c->d_text[b], len, cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+        return SLOTH_OK;
+    };
+    rc = enqueue_overlapped(
+        c, rots, n_frames,
+        [&](size_t k) -> int {   // buffers k&1 (cells and text) must have been copied out (frame k-2)
+            if (k >= 2) CU(cudaStreamWaitEvent(c->resolve_stream, c->ev_copied[k & 1], 0));
+            return SLOTH_OK;
+        },
+        [&](size_t k) { return c->d_cells[k & 1]; },
+        [&](size_t k) -> int {
+            const int b = (int)(k & 1);
+            int r = enqueue_flush(c, mode, c->d_cells[b], cpf, c->d_text[b], c->d_text_total + b, c->flush_block_sum,
+                                  c->flush_block_off, c->resolve_stream);
+            if (r) return r;
+            CU(cudaMemcpyAsync(c->h_text_total + b, c->d_text_total + b, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                               c->resolve_stream));
+            CU(cudaEventRecord(c->ev_text[b], c->resolve_stream));
+            return k >= 1 ? finish(k - 1) : SLOTH_OK;
+        });
+    if (rc) return rc;
+    rc = finish(n_frames - 1);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->resolve_stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    c->last_was_batch = true;
+    c->ev_valid = false;
+    return SLOTH_OK;
+}
+
+int sloth_render_text(sloth_ctx* c, const float rot[16], int mode, char* text_out, size_t cap, size_t* len_out)
+{
+    if (!len_out) return fail(SLOTH_E_ARG, "len_out is null");
+    return sloth_render_text_batch(c, rot, 1, mode, text_out, cap, len_out);
 }
 
 int sloth_shader_set(sloth_ctx* c, const float thr[9], const char glyph[10])

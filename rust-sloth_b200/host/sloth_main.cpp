@@ -5,7 +5,8 @@
 //                         [-z/--roll f] [-b] [image -w W [-h H] [-j/--webify N] [-x -y -z -b]]`
 //   src/main.rs:25-114    frame loop: interactive (raw mode, 500 fps cap, q / Ctrl-C), `image`
 //                         single shot, `image -j N` JS-frame export
-//   src/context.rs:50-92  flush: plain glyphs / ANSI truecolor per cell / <span> per cell
+//   src/context.rs:50-92  flush: plain glyphs / ANSI truecolor per cell / <span> per cell -- serialised on
+//                         the GPU (sloth_render_text*), the host only adds the frame prefixes/suffixes
 // The per-frame group update + clear + draw_mesh (main.rs:78-83) is one sloth_render call.
 // Quirks kept on purpose: only the first positional value is read and split on ' '
 // (inputs.rs:97); in image mode the rotation flags are taken from the sub-command only
@@ -113,29 +114,6 @@ void check(int rc)
     }
 }
 
-// Context::flush, context.rs:50-92
-void flush_cells(const std::vector<uint32_t>& cells, bool image, bool color, bool webify, std::string& out)
-{
-    if (!image) out += "\x1b[1;1H";            // cursor::MoveTo(0,0)
-    char buf[96];
-    if (!color) {
-        for (uint32_t c : cells) out.push_back((char)(c & 0xFF));
-        out.push_back('\n');                   // println!
-    } else if (webify) {
-        for (uint32_t c : cells) {
-            int n = std::snprintf(buf, sizeof buf, "<span style=\"color:rgb(%u,%u,%u)\">%c", (c >> 8) & 0xFF,
-                                  (c >> 16) & 0xFF, (c >> 24) & 0xFF, (char)(c & 0xFF));
-            out.append(buf, n);
-        }
-    } else {                                   // crossterm 0.18 styled content: bg, fg, char, reset
-        for (uint32_t c : cells) {
-            int n = std::snprintf(buf, sizeof buf, "\x1b[48;2;25;25;25m\x1b[38;2;%u;%u;%um%c\x1b[0m", (c >> 8) & 0xFF,
-                                  (c >> 16) & 0xFF, (c >> 24) & 0xFF, (char)(c & 0xFF));
-            out.append(buf, n);
-        }
-    }
-}
-
 termios g_saved;
 bool g_raw = false;
 void leave_raw()
@@ -207,10 +185,8 @@ int main(int argc, char** argv)
     check(sloth_ctx_create(0, image ? 1 : 0, &ctx));
     check(sloth_scene_set(ctx, xyz.data(), rgb.data(), rgb.size() / 3, sloth::scene_scale0(meshes)));
 
-    std::string out;
     if (image) {
         check(sloth_ctx_resize(ctx, W, H));
-        const size_t cpf = sloth_cells_per_frame(ctx);
         if (webify) {
             // main.rs:55-58,85-106: all frames are known up front -> one batched call
             const size_t cap = (size_t)(webify_todo > 0 ? webify_todo : 1) + 4;
@@ -222,30 +198,34 @@ int main(int argc, char** argv)
             std::vector<float> rots(n * 16);
             for (size_t k = 0; k < n; ++k) sloth_rotation_from_euler(turntable[0], pitches[k], turntable[2], &rots[k * 16]);
             std::fputs("let frames = [\n", stdout);
-            const size_t chunk = 8;            // frames per batched call (bounded host memory)
+            // Context::flush runs on the GPU (sloth_render_text_batch): the host only frames the text
+            const int mode = no_color ? 0 : 2;
+            const size_t text_cap = sloth_text_capacity(ctx, mode);
+            const size_t stride = (text_cap + 63) & ~(size_t)63;
+            const size_t chunk = std::max<size_t>(1, std::min<size_t>(8, ((size_t)512 << 20) / stride));
             void* pinned = nullptr;
-            check(sloth_pinned_alloc(chunk * cpf * sizeof(uint32_t), &pinned));
-            std::vector<uint32_t> cells(cpf);
+            check(sloth_pinned_alloc(chunk * stride, &pinned));
+            std::vector<size_t> lens(chunk);
             for (size_t k0 = 0; k0 < n; k0 += chunk) {
                 const size_t m = std::min(chunk, n - k0);
-                check(sloth_render_batch(ctx, &rots[k0 * 16], m, (uint32_t*)pinned));
+                check(sloth_render_text_batch(ctx, &rots[k0 * 16], m, mode, (char*)pinned, stride, lens.data()));
                 for (size_t k = 0; k < m; ++k) {
-                    cells.assign((uint32_t*)pinned + k * cpf, (uint32_t*)pinned + (k + 1) * cpf);
-                    out.clear();
-                    out += "`\n";
-                    flush_cells(cells, true, !no_color, true, out);
-                    out += (k0 + k == n - 1) ? "`];\n" : "`,\n";
-                    std::fwrite(out.data(), 1, out.size(), stdout);
+                    std::fputs("`\n", stdout);
+                    std::fwrite((char*)pinned + k * stride, 1, lens[k], stdout);
+                    if (no_color) std::fputc('\n', stdout);            // println! of the plain frame
+                    std::fputs((k0 + k == n - 1) ? "`];\n" : "`,\n", stdout);
                 }
             }
             sloth_pinned_free(pinned);
         } else {
             float rot[16];
             sloth_rotation_from_euler(turntable[0], turntable[1], turntable[2], rot);
-            std::vector<uint32_t> cells(cpf);
-            check(sloth_render(ctx, rot, cells.data(), nullptr));
-            flush_cells(cells, true, !no_color, false, out);
-            std::fwrite(out.data(), 1, out.size(), stdout);
+            const int mode = no_color ? 0 : 1;
+            std::vector<char> text(sloth_text_capacity(ctx, mode) + 1);
+            size_t len = 0;
+            check(sloth_render_text(ctx, rot, mode, text.data(), text.size(), &len));
+            std::fwrite(text.data(), 1, len, stdout);
+            if (no_color) std::fputc('\n', stdout);
         }
         std::fflush(stdout);
         sloth_ctx_destroy(ctx);
@@ -263,7 +243,7 @@ int main(int argc, char** argv)
     std::fputs("\x1b[?25l", stdout);           // cursor::Hide
     const double target_frame_time = 1.0 / 500.0;   // fps_cap = 500
     uint32_t cw = 0, ch = 0;
-    std::vector<uint32_t> cells;
+    std::vector<char> text;
     for (;;) {
         auto last = std::chrono::steady_clock::now();
         pollfd pfd{STDIN_FILENO, POLLIN, 0};
@@ -277,14 +257,16 @@ int main(int argc, char** argv)
             check(sloth_ctx_resize(ctx, tw, th));
             cw = tw;
             ch = th;
-            cells.resize(sloth_cells_per_frame(ctx));
         }
         float rot[16];
         sloth_rotation_from_euler(turntable[0], turntable[1], turntable[2], rot);
-        check(sloth_render(ctx, rot, cells.data(), nullptr));
-        out.clear();
-        flush_cells(cells, false, !no_color, false, out);
-        std::fwrite(out.data(), 1, out.size(), stdout);
+        const int mode = no_color ? 0 : 1;
+        text.resize(sloth_text_capacity(ctx, mode) + 1);
+        size_t len = 0;
+        check(sloth_render_text(ctx, rot, mode, text.data(), text.size(), &len));
+        std::fputs("\x1b[1;1H", stdout);         // cursor::MoveTo(0,0), context.rs:53-55
+        std::fwrite(text.data(), 1, len, stdout);
+        if (no_color) std::fputc('\n', stdout);
         std::fflush(stdout);
         const float dt = (float)std::chrono::duration_cast<std::chrono::nanoseconds>(
                              std::chrono::steady_clock::now() - last).count() / 1000000000.0f;

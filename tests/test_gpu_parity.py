@@ -269,3 +269,25 @@ def test_device_batch_overlap_equals_single_frames():
             ocells, _, _ = oracle.render(xyz, rgb, s0, W, H, rots[k], mode=1)
             assert np.array_equal(single, ocells)
         ctx.close()
+
+
+def test_device_flush_is_byte_exact():
+    """GPU-side Context::flush (plain / ANSI / <span>) == the host formatter, byte for byte."""
+    xyz, rgb, s0 = S.soup("vaporeon")                      # per-triangle colours: all digit counts occur
+    rng = np.random.default_rng(7)
+    rgb = rng.choice(np.array([0, 5, 9, 10, 42, 99, 100, 163, 255], np.uint8), size=rgb.shape)
+    pitches = oracle.turntable(0.0, 5)
+    rots = np.stack([oracle.rotation(0.0, p, 0.2) for p in pitches])
+    for (W, H) in [(200, 100), (131, 77), (33, 5)]:
+        ctx = rs.Context.blank(True)
+        ctx.set_scene(xyz, rgb, s0)
+        ctx.resize(W, H)
+        frames = ctx.render_batch(rots).copy()
+        for mode, (color, webify) in {0: (False, False), 1: (True, False), 2: (True, True)}.items():
+            texts = ctx.render_text_batch(rots, mode)
+            for k in range(len(rots)):
+                want = rs.flush_bytes(frames[k], color, webify, True)
+                if mode == 0:
+                    want = want[:-1]                       # println's newline is the host's
+                assert texts[k] == want, f"{W}x{H} mode {mode} frame {k}"
+        ctx.close()
