@@ -329,6 +329,21 @@ def run_b200(args, rank, local_rank, world):
 
 
 def main():
+    # Only the final JSON line may reach stdout: libraries (NCCL prints its version banner there when
+    # NCCL_DEBUG is set in the environment) write to fd 1 behind Python's back, so fd 1 is pointed at
+    # stderr for the whole run and the saved descriptor is used for the one line that matters.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global print
+    _print = print
+
+    def print(*a, **k):  # noqa: A001 - shadows the builtin on purpose for the JSON line
+        if k.get("file") is None:
+            os.write(saved_stdout, (" ".join(str(x) for x in a) + "\n").encode())
+        else:
+            _print(*a, **k)
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=64)

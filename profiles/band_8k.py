@@ -13,13 +13,21 @@ import torch.distributed as dist
 import rust_sloth_b200 as rs
 from rust_sloth_b200 import meshes, multigpu
 
-freq = int(sys.argv[1]) if len(sys.argv) > 1 else 708
+scene = sys.argv[1] if len(sys.argv) > 1 else "708"     # icosphere frequency, or the name of a bundled soup
 W, H = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (7680, 4320)
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-xyz, rgb, s0 = meshes.icosphere(freq)
+if scene.isdigit():
+    freq = int(scene)
+    xyz, rgb, s0 = meshes.icosphere(freq)
+    label = f"icosphere f={freq}"
+else:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scenes as S
+    xyz, rgb, s0 = S.soup(scene)
+    label = scene
 ctx = rs.Context.blank(True, device=local)
 ctx.set_scene(xyz, rgb, s0)
 br = multigpu.BandRenderer(ctx, W, H, rank, world)
@@ -51,7 +59,7 @@ if rank == 0:
     ref, _ = whole.render(rots[5])
     ok = bool(np.array_equal(ref, frame))
     whole.close()
-    print(json.dumps({"workload": f"icosphere f={freq} ({len(xyz)} triangles) at {W}x{H}, one frame in {world} row bands",
+    print(json.dumps({"workload": f"{label} ({len(xyz)} triangles) at {W}x{H}, one frame in {world} row bands",
                       "n_gpus": world, "frames_per_s": K / (float(ms[0]) * 1e-3), "ms_per_frame": float(ms[0]) / K,
                       "gather_bytes_per_gpu": 4 * W * H // world, "banded_equals_whole_frame": ok}))
 if world > 1:
