@@ -291,3 +291,32 @@ def test_device_flush_is_byte_exact():
                     want = want[:-1]                       # println's newline is the host's
                 assert texts[k] == want, f"{W}x{H} mode {mode} frame {k}"
         ctx.close()
+
+
+def test_error_codes_and_call_order():
+    ctx = rs.Context.blank(True)
+    rot = oracle.rotation(0.0, S.PI, 0.0)
+    with pytest.raises(rs.SlothError) as e:
+        ctx.render(rot)
+    assert e.value.code == rs.SLOTH_E_STATE                       # no scene yet
+    xyz, rgb, s0 = S.soup("cube")
+    ctx.set_scene(xyz, rgb, s0)
+    ctx.width, ctx.height = 0, 0
+    with pytest.raises(rs.SlothError) as e:
+        ctx.render(rot)
+    assert e.value.code == rs.SLOTH_E_STATE                       # no size yet
+    for (W, H, code) in [(0, 10, rs.SLOTH_E_ARG), (70000, 10, rs.SLOTH_E_TOO_LARGE), (65535, 65535, rs.SLOTH_E_TOO_LARGE)]:
+        with pytest.raises(rs.SlothError) as e:
+            ctx.resize(W, H)
+        assert e.value.code == code
+    ctx.resize(40, 20)
+    with pytest.raises(rs.SlothError) as e:
+        ctx.set_band(10, 30)
+    assert e.value.code == rs.SLOTH_E_ARG
+    cells, _ = ctx.render(rot)
+    ocells, _, _ = oracle.render(xyz, rgb, s0, 40, 20, rot)
+    assert np.array_equal(cells, ocells)                          # the context still works after the errors
+    ctx.close()
+    with pytest.raises(rs.SlothError) as e:
+        rs.Context.blank(True, device=999)
+    assert e.value.code == rs.SLOTH_E_ARG
