@@ -273,23 +273,21 @@ __global__ void __launch_bounds__(G3_WARPS * 32, G3_BLOCKS_PER_SM) k_geom3(const
             // rowmax[y] = max(c + 1) over chunks c that stamp row y.  The lanes of a chunk are
             // neighbours on screen, so their rows fall into a 64-row window: two REDUX.OR give
             // the chunk's row set, then lane i owns rows i and 32+i of the window (conflict-free).
+            // Branch-free: with nothing to stamp the need words are 0 and no atomic is issued.
+            const uint32_t sy0 = BAND ? max(miny, p.row0) : miny, sy1 = BAND ? min(maxy, p.row1) : maxy;
+            const bool st = do_stamps && has_rows && sy0 < sy1;
+            bool tall = false;   // rows outside the 64-row window: stamped in the rare block below
             if (do_stamps) {
-                const uint32_t sy0 = BAND ? max(miny, p.row0) : miny, sy1 = BAND ? min(maxy, p.row1) : maxy;
-                const bool st = has_rows && sy0 < sy1;
                 const uint32_t ymin = __reduce_min_sync(0xFFFFFFFFu, st ? sy0 : 0xFFFFFFFFu);
-                if (ymin != 0xFFFFFFFFu) {
-                    const uint32_t base = ymin & ~31u;
-                    const uint32_t lo = sy0 - base, n = sy1 - sy0;          // meaningful when st
-                    const bool fits = st && n <= 32u && lo + n <= 64u;      // inside the 2-word window
-                    unsigned long long m64 = 0ull;
-                    if (fits) m64 = (unsigned long long)(0xFFFFFFFFu >> (32u - n)) << lo;
-                    const uint32_t need0 = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)m64);
-                    const uint32_t need1 = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(m64 >> 32));
-                    if ((need0 >> lane) & 1u) atomicMax(rowmax + base + lane, c + 1u);
-                    if ((need1 >> lane) & 1u) atomicMax(rowmax + base + 32u + lane, c + 1u);
-                    if (st && !fits)   // tall or far-away triangle: row by row
-                        for (uint32_t y = sy0; y < sy1; ++y) atomicMax(rowmax + y, c + 1u);
-                }
+                const uint32_t base = ymin & ~31u;
+                const uint32_t lo = sy0 - base, n = sy1 - sy0;              // meaningful when st
+                const bool fits = st && n <= 32u && lo + n <= 64u;          // inside the 2-word window
+                tall = st && !fits;
+                const unsigned long long m64 = fits ? (unsigned long long)(0xFFFFFFFFu >> ((32u - n) & 31u)) << (lo & 63u) : 0ull;
+                const uint32_t need0 = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)m64);
+                const uint32_t need1 = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(m64 >> 32));
+                if ((need0 >> lane) & 1u) atomicMax(rowmax + base + lane, c + 1u);
+                if ((need1 >> lane) & 1u) atomicMax(rowmax + base + 32u + lane, c + 1u);
             }
 
             // ---- classification ---------------------------------------------------------------
@@ -302,21 +300,14 @@ __global__ void __launch_bounds__(G3_WARPS * 32, G3_BLOCKS_PER_SM) k_geom3(const
             const float dx2 = sub(x2, x1), dy2 = sub(y2, y1);
             const bool cand = live && regular && !backface_proven(p, dx1, dy1, dx2, dy2, mn0, mx0, mn1, mx1);
             const uint32_t rows = maxy - miny, span = maxx - minx;
-            uint32_t tw;
-            {
-                const uint32_t f = __float2uint_rz(floorf(mx0));
-                const uint32_t te = f >= maxx ? maxx : f + 1u;
-                tw = te > minx ? te - minx : 0u;
-            }
-            const bool foot = cand && rows <= 2u && tw <= 2u;                  // tier 1: 2 x 3 footprint, lockstep
-            const bool mid = cand && !foot && rows <= 8u && tw <= 6u;           // tier 2: up to 8 x 8, per-lane loop
-            uint32_t walk_items = 0;                                            // tier 3: k_walk
-            if (cand && !foot && !mid) walk_items = (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw);
+            // tight width <= 2  <=>  span <= 2 or floor(max_x) <= minx + 1   (see tight_width)
+            const bool foot = cand && rows <= 2u && (span <= 2u || __float2uint_rz(floorf(mx0)) <= minx + 1u);   // tier 1
+            bool beyond = cand && !foot;   // tier 2 / 3: handled in the rare block
 
-            // ---- phase B: 2 x 3 footprint in registers ----------------------------------------
-            uint32_t mask = 0;
+            // ---- tier 1: 2 x 3 footprint in registers, lockstep ---------------------------------
+            uint32_t mask = 0, mask_hi = 0;
+            bool wide = false;   // footprint bits are row*8 + col (tier 2) instead of row*3 + col
             if (__any_sync(0xFFFFFFFFu, foot)) {
-                const bool nd0 = !(dy0 < 0.0f), nd1 = !(dy1 < 0.0f), nd2 = !(dy2 < 0.0f);
                 float cr[2][3], gc[3][3];
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
@@ -332,30 +323,47 @@ __global__ void __launch_bounds__(G3_WARPS * 32, G3_BLOCKS_PER_SM) k_geom3(const
                     gc[k][1] = mul(dy1, sub(px, x3));
                     gc[k][2] = mul(dy2, sub(px, x1));
                 }
-                bool open = false;   // some active row is not provably finished after column 2
+                uint32_t cov = 0;
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
+                for (int r = 0; r < 2; ++r)
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const bool n0 = sub(cr[r][0], gc[k][0]) < 0.0f;
-                        const bool n1 = sub(cr[r][1], gc[k][1]) < 0.0f;
-                        const bool n2 = sub(cr[r][2], gc[k][2]) < 0.0f;
                         // regular triangle: no NaN, so "all >= 0" == "none < 0"
-                        if (!(n0 || n1 || n2) && (uint32_t)r < rows && (uint32_t)k < span) mask |= 1u << (r * 3 + k);
-                        if (k == 2 && (uint32_t)r < rows && span > 3u && !((n0 && nd0) || (n1 && nd1) || (n2 && nd2)))
-                            open = true;
+                        const float w0 = sub(cr[r][0], gc[k][0]), w1 = sub(cr[r][1], gc[k][1]), w2 = sub(cr[r][2], gc[k][2]);
+                        if (!(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f)) cov |= 1u << (r * 3 + k);
+                    }
+                // candidates that exist: rows r < rows, columns k < span
+                const uint32_t cm = (1u << min(span, 3u)) - 1u;
+                const uint32_t valid = cm | (rows > 1u ? cm << 3 : 0u);
+                // a row is finished after column 2 if a closing edge (dy >= 0) fails there
+                bool open = false;
+                if (span > 3u) {
+                    const bool nd0 = !(dy0 < 0.0f), nd1 = !(dy1 < 0.0f), nd2 = !(dy2 < 0.0f);
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const bool closed = (nd0 && sub(cr[r][0], gc[2][0]) < 0.0f) || (nd1 && sub(cr[r][1], gc[2][1]) < 0.0f) ||
+                                            (nd2 && sub(cr[r][2], gc[2][2]) < 0.0f);
+                        if ((uint32_t)r < rows && !closed) open = true;
                     }
                 }
-                if (!foot) mask = 0;
-                else if (open) {   // sliver: hand the whole triangle to k_walk (exact, any width)
-                    mask = 0;
-                    walk_items = (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw);
+                if (foot) {
+                    if (open) beyond = true;   // sliver: the rare block hands it to k_tail
+                    else mask = cov & valid;
                 }
             }
 
-            // ---- tier 2: triangles up to 8 rows x (6 + closing) columns, one lane each ----------
-            uint32_t mask_hi = 0;
-            if (__any_sync(0xFFFFFFFFu, mid)) {
+            // ---- everything uncommon under one vote: tier 2, tier 3 / irregular queues, tall stamps ----
+            if (__any_sync(0xFFFFFFFFu, beyond || tall || (CHECK_REGULAR && live && !regular))) {
+                if (tall)
+                    for (uint32_t y = sy0; y < sy1; ++y) atomicMax(rowmax + y, c + 1u);
+                uint32_t tw;
+                {
+                    const uint32_t f = __float2uint_rz(floorf(mx0));
+                    const uint32_t te = f >= maxx ? maxx : f + 1u;
+                    tw = te > minx ? te - minx : 0u;
+                }
+                bool walk = beyond;
+                const bool mid = beyond && !foot && rows <= 8u && tw <= 6u;   // tier 2: up to 8 x 8, one lane each
                 if (mid) {
                     Setup s;
                     s.x1 = x1; s.y1 = y1; s.x2 = x2; s.y2 = y2; s.x3 = x3; s.y3 = y3;
@@ -373,61 +381,60 @@ __global__ void __launch_bounds__(G3_WARPS * 32, G3_BLOCKS_PER_SM) k_geom3(const
                         }
                         open = !closed && span > 8u;   // candidates remain right of the window
                     }
-                    if (open) walk_items = (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw);
-                    else { mask = (uint32_t)m; mask_hi = (uint32_t)(m >> 32); }
+                    if (!open) { mask = (uint32_t)m; mask_hi = (uint32_t)(m >> 32); wide = true; walk = false; }
+                }
+                // tier 3: row-band work items for k_tail, one warp-aggregated atomic
+                const uint32_t walk_items = walk ? (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw) : 0u;
+                const unsigned need = __ballot_sync(0xFFFFFFFFu, walk_items > 0);
+                if (need) {
+                    uint32_t wi = walk_items;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t nn = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                        if ((int)lane >= d) wi += nn;
+                    }
+                    const uint32_t total = __shfl_sync(0xFFFFFFFFu, wi, 31);
+                    unsigned long long old = 0;
+                    if (lane == 0)
+                        old = atomicAdd(&q.aux->walk_counter, ((unsigned long long)__popc(need) << ITEM_BITS) | total);
+                    old = __shfl_sync(0xFFFFFFFFu, old, 0);
+                    if (walk_items > 0) {
+                        const uint32_t slot = (uint32_t)(old >> ITEM_BITS) + __popc(need & ((1u << lane) - 1u));
+                        q.walk_tri[slot] = t;
+                        q.walk_base[slot] = (old & ITEM_MASK) + (wi - walk_items);
+                    }
+                }
+                if (CHECK_REGULAR) {
+                    const unsigned irr = __ballot_sync(0xFFFFFFFFu, live && !regular);
+                    if (irr) {
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&q.aux->irr_count, (uint32_t)__popc(irr));
+                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                        if (live && !regular) q.irr_tri[base + __popc(irr & ((1u << lane) - 1u))] = t;
+                    }
                 }
             }
 
             // ---- phase C: park covering triangles; emit 32 at a time --------------------------
-            const unsigned cov = __ballot_sync(0xFFFFFFFFu, (mask | mask_hi) != 0u);
-            if (cov) {
+            const unsigned cov_lanes = __ballot_sync(0xFFFFFFFFu, (mask | mask_hi) != 0u);
+            if (cov_lanes) {
                 if (mask | mask_hi) {
-                    const uint32_t slot = (q_head + q_count + __popc(cov & ((1u << lane) - 1u))) & (G3_RING - 1u);
+                    const uint32_t slot = (q_head + q_count + __popc(cov_lanes & ((1u << lane) - 1u))) & (G3_RING - 1u);
                     wq.raw[0][slot] = v0; wq.raw[1][slot] = v1; wq.raw[2][slot] = v2;
                     wq.raw[3][slot] = v3; wq.raw[4][slot] = v4; wq.raw[5][slot] = v5;
                     wq.raw[6][slot] = v6; wq.raw[7][slot] = v7; wq.raw[8][slot] = v8;
-                    wq.tri[slot] = t | (mid ? 0x80000000u : 0u);
+                    wq.tri[slot] = t | (wide ? 0x80000000u : 0u);   // bit 31: tier-2 (8 x 8) footprint
                     wq.xy[slot] = minx | (miny << 16);
                     wq.mask_lo[slot] = mask;
                     wq.mask_hi[slot] = mask_hi;
                 }
-                q_count += __popc(cov);
+                q_count += __popc(cov_lanes);
                 if (q_count >= 32u) {
                     __syncwarp();
                     g3_emit(p, wq, q_head, 32u, lane, keys, nfrag_count);
                     __syncwarp();
                     q_head = (q_head + 32u) & (G3_RING - 1u);
                     q_count -= 32u;
-                }
-            }
-
-            // ---- rare: queue pushes for k_walk / k_irregular (one atomic per warp) ------------
-            const unsigned need = __ballot_sync(0xFFFFFFFFu, walk_items > 0);
-            if (need) {
-                uint32_t wi = walk_items;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-                    if ((int)lane >= d) wi += n;
-                }
-                const uint32_t total = __shfl_sync(0xFFFFFFFFu, wi, 31);
-                unsigned long long old = 0;
-                if (lane == 0)
-                    old = atomicAdd(&q.aux->walk_counter, ((unsigned long long)__popc(need) << ITEM_BITS) | total);
-                old = __shfl_sync(0xFFFFFFFFu, old, 0);
-                if (walk_items > 0) {
-                    const uint32_t slot = (uint32_t)(old >> ITEM_BITS) + __popc(need & ((1u << lane) - 1u));
-                    q.walk_tri[slot] = t;
-                    q.walk_base[slot] = (old & ITEM_MASK) + (wi - walk_items);
-                }
-            }
-            if (CHECK_REGULAR) {
-                const unsigned irr = __ballot_sync(0xFFFFFFFFu, live && !regular);
-                if (irr) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&q.aux->irr_count, (uint32_t)__popc(irr));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (live && !regular) q.irr_tri[base + __popc(irr & ((1u << lane) - 1u))] = t;
                 }
             }
         }
