@@ -80,6 +80,7 @@ struct sloth_ctx {
     uint32_t* sc_rgb = nullptr;
     float* sc_chunks = nullptr;      // TMA feed: 1280-byte chunks of 32 triangles
     uint32_t geom_blocks_per_sm = G3_BLOCKS_PER_SM;   // SLOTH_GRID overrides (profiling)
+    uint32_t tail_blocks_per_sm = 8;  // SLOTH_TAIL overrides (profiling)
     bool tma_feed = false;           // SLOTH_TMA=1 feeds k_geom3 through cp.async.bulk + mbarrier (measured 3 % slower)
     uint32_t n_tri = 0;
     float scene_max = 0.0f;
@@ -247,7 +248,10 @@ int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t s
             kern<<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->sc_chunks, c->keys[set], q, batch_chunks, rowmax_shared);
         }
         if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
-        k_tail<<<c->sm_count * 8 + c->sm_count, 128, 0, st>>>(p, sc, c->keys[set], q, (uint32_t)c->sm_count * 8u);
+        {
+            const uint32_t wb = (uint32_t)c->sm_count * c->tail_blocks_per_sm, ib = std::max<uint32_t>(1u, (uint32_t)c->sm_count / 2u);
+            k_tail<<<wb + ib, 128, 0, st>>>(p, sc, c->keys[set], q, wb);
+        }
         if (kt) CU(cudaEventRecord(c->ev[EV_WALK], st));
         c->launches += 2;
     } else if (kt) {
@@ -418,6 +422,7 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     c->sm_count = prop.multiProcessorCount;
     if (const char* g = std::getenv("SLOTH_DEBUG")) c->debug = (uint32_t)std::atoi(g);
     if (const char* g = std::getenv("SLOTH_TMA")) c->tma_feed = std::atoi(g) != 0;
+    if (const char* g = std::getenv("SLOTH_TAIL")) c->tail_blocks_per_sm = (uint32_t)std::max(1, std::atoi(g));
     if (const char* g = std::getenv("SLOTH_GRID")) c->geom_blocks_per_sm = (uint32_t)std::max(1, std::atoi(g));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
