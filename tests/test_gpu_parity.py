@@ -320,3 +320,47 @@ def test_error_codes_and_call_order():
     with pytest.raises(rs.SlothError) as e:
         rs.Context.blank(True, device=999)
     assert e.value.code == rs.SLOTH_E_ARG
+
+
+def test_full_size_baseline_configs_bit_exact():
+    """BASELINE configs at their full size.  The 10M-triangle icosphere at 3840x2160 is checked against the
+    oracle's row-terminating mode (mode 1, itself validated against the faithful scan on every smaller case;
+    the faithful scan would take ~20 s here); 'suzy suzy' at 3840x2160 (every fragment of the second copy is
+    an exact depth tie) and skull at 1920x1080 against the faithful scan."""
+    xyz, rgb, s0 = meshes.icosphere(708)
+    assert len(xyz) == 10_025_280
+    rot = oracle.rotation(0.0, oracle.turntable(0.0, 64)[5], 0.0)
+    ocells, oz, ocnt = oracle.render(xyz, rgb, s0, 3840, 2160, rot, mode=1)
+    cells, z, st = gpu_frame(xyz, rgb, s0, 3840, 2160, rot)
+    assert_same(cells, z, ocells, oz, "icosphere f=708 4K")
+    assert st["fragments"] == ocnt["covered"]
+    for scene, W, H in [("suzy_suzy", 3840, 2160), ("skull", 1920, 1080)]:
+        xyz, rgb, s0 = S.soup(scene)
+        rot = oracle.rotation(0.0, S.PI, 0.0)
+        ocells, oz, ocnt = oracle.render(xyz, rgb, s0, W, H, rot, mode=0)
+        cells, z, st = gpu_frame(xyz, rgb, s0, W, H, rot)
+        assert_same(cells, z, ocells, oz, f"{scene} {W}x{H}")
+        assert st["fragments"] == ocnt["covered"]
+    # depth-tie property of "suzy suzy": the second copy never wins a cell
+    xyz1, rgb1, s01 = S.soup("suzy")
+    one, _, _ = gpu_frame(xyz1, rgb1, s01, 3840, 2160, rot)
+    two, _, _ = gpu_frame(np.concatenate([xyz1, xyz1]), np.concatenate([rgb1, 255 - rgb1]), s01, 3840, 2160, rot)
+    assert np.array_equal(one, two)
+
+
+def test_tma_feed_variant_is_bit_exact(monkeypatch):
+    """SLOTH_TMA=1: k_geom3 fed by cp.async.bulk + mbarrier (off by default: measured 3 % slower)."""
+    monkeypatch.setenv("SLOTH_TMA", "1")
+    for f, (W, H) in [(24, (160, 80)), (90, (640, 360))]:
+        xyz, rgb, s0 = meshes.icosphere(f)
+        for k in range(2):
+            rot = oracle.rotation(0.3 * k, np.float32(np.pi) + 0.5 * k, 0.0)
+            ocells, oz, ocnt = oracle.render(xyz, rgb, s0, W, H, rot, mode=1)
+            cells, z, st = gpu_frame(xyz, rgb, s0, W, H, rot)
+            assert_same(cells, z, ocells, oz, f"tma icosphere f={f}")
+            assert st["fragments"] == ocnt["covered"]
+    xyz, rgb, s0 = meshes.random_soup(11, 50)
+    rot = oracle.rotation(0.2, 3.0, 0.1)
+    ocells, oz, _ = oracle.render(xyz, rgb, s0, 101, 57, rot, mode=0)
+    cells, z, _ = gpu_frame(xyz, rgb, s0, 101, 57, rot)
+    assert_same(cells, z, ocells, oz, "tma fuzz")
