@@ -495,7 +495,7 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
     CU(cudaMalloc(&c->sc_z3, n * sizeof(float)));
     CU(cudaMalloc(&c->sc_rgb, n * sizeof(uint32_t)));
     const size_t n_padded = (n + 31) & ~(size_t)31;
-    CU(cudaMalloc(&c->sc_chunks, n_padded / 32 * CHUNK_BYTES));
+    if (c->tma_feed) CU(cudaMalloc(&c->sc_chunks, n_padded / 32 * CHUNK_BYTES));   // second copy only for the TMA feed
     CU(cudaMalloc(&c->walk_tri, n * sizeof(uint32_t)));
     CU(cudaMalloc(&c->walk_base, n * sizeof(unsigned long long)));
     CU(cudaMalloc(&c->irr_tri, n * sizeof(uint32_t)));
@@ -507,8 +507,9 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
         CU(cudaMemcpyAsync(d_xyz, xyz, n_tri * 9 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(d_rgb, rgb, n_tri * 3, cudaMemcpyHostToDevice, c->stream));
         k_pack_scene<<<(unsigned)((n_tri + 255) / 256), 256, 0, c->stream>>>(d_xyz, d_rgb, (uint32_t)n_tri, c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb);
-        k_pack_chunks<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(c->sc_a, c->sc_b, c->sc_z3, (uint32_t)n_tri, (uint32_t)n_padded, c->sc_chunks);
-        c->launches += 2;
+        if (c->tma_feed)
+            k_pack_chunks<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(c->sc_a, c->sc_b, c->sc_z3, (uint32_t)n_tri, (uint32_t)n_padded, c->sc_chunks);
+        c->launches += c->tma_feed ? 2 : 1;
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(c->stream));
         cudaFree(d_xyz);

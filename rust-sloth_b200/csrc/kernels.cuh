@@ -1,7 +1,8 @@
 // kernels.cuh -- the per-frame kernels of the sloth raster path (sm_100a).
 //
-// Frame pipeline (one stream, no host round-trips, 3 launches + one small memset):
-//   k_geom3    persistent warps over the triangle stream: coalesced 16+16+8 B loads with register
+// Frame pipeline (no host round-trips, 3 launches + one small memset; in batches the geometry of
+// frame k+1 runs on one stream while the resolve of frame k runs on a second one):
+//   k_geom3    persistent warps over the triangle stream: coalesced 16+16+4 B loads with register
 //              prefetch, transform, bounds, image-mode row stamps, back-face proof; triangles up to
 //              8x8 candidates are rasterised in place (64-bit atomicMin into the key plane), larger
 //              ones are queued as row-band work items, non-finite ones for the brute-force pass

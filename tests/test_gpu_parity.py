@@ -364,3 +364,26 @@ def test_tma_feed_variant_is_bit_exact(monkeypatch):
     ocells, oz, _ = oracle.render(xyz, rgb, s0, 101, 57, rot, mode=0)
     cells, z, _ = gpu_frame(xyz, rgb, s0, 101, 57, rot)
     assert_same(cells, z, ocells, oz, "tma fuzz")
+
+
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+_coord = st.one_of(
+    st.floats(min_value=-1.5, max_value=1.5, width=32),
+    st.sampled_from([0.0, -0.0, 1.0, -1.0, 0.5, 0.25, 1e-30, -1e-30, 1e-45, 3e38, -3e38, float("inf"), float("-inf"), float("nan")]))
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
+@given(tris=st.lists(st.lists(_coord, min_size=9, max_size=9), min_size=1, max_size=40),
+       W=st.integers(min_value=1, max_value=70), H=st.integers(min_value=1, max_value=40),
+       angles=st.tuples(st.floats(-7, 7, width=32), st.floats(-7, 7, width=32), st.floats(-7, 7, width=32)),
+       image=st.booleans(), s0=st.sampled_from([1.0, 0.7, 2.5, 0.0]))
+def test_hypothesis_fuzz_gpu_vs_oracle(tris, W, H, angles, image, s0):
+    """Arbitrary small soups incl. NaN / inf / denormal / huge coordinates, 1-cell frames, odd widths."""
+    xyz = np.array(tris, np.float32)
+    rgb = (np.arange(xyz.shape[0] * 3, dtype=np.int64) * 37 % 256).astype(np.uint8).reshape(-1, 3)
+    rot = oracle.rotation(*angles)
+    ocells, oz, ocnt = oracle.render(xyz, rgb, s0, W, H, rot, image=image, mode=0)
+    cells, z, st_ = gpu_frame(xyz, rgb, np.float32(s0), W, H, rot, image=image)
+    assert_same(cells, z, ocells, oz, "hypothesis")
+    assert st_["fragments"] == ocnt["covered"]

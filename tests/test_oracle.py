@@ -197,3 +197,30 @@ def test_sampling_partitions_the_triangle_list():
     parts = [oracle.render(xyz, rgb, s0, 120, 60, rot, tri_first=i, tri_step=4)[2] for i in range(4)]
     assert sum(p["candidates"] for p in parts) == full["candidates"]
     assert sum(p["covered"] for p in parts) == full["covered"]
+
+
+# ---- property fuzz (hypothesis): the three CPU statements of the algorithm agree -----------------
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+_coord = st.one_of(
+    st.floats(min_value=-1.5, max_value=1.5, width=32),
+    st.sampled_from([0.0, -0.0, 1.0, -1.0, 0.5, 0.25, 1e-30, -1e-30, 1e-45, 3e38, -3e38, float("inf"), float("-inf"), float("nan")]))
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(tris=st.lists(st.lists(_coord, min_size=9, max_size=9), min_size=1, max_size=6),
+       W=st.integers(min_value=1, max_value=40), H=st.integers(min_value=1, max_value=24),
+       angles=st.tuples(st.floats(-7, 7, width=32), st.floats(-7, 7, width=32), st.floats(-7, 7, width=32)),
+       image=st.booleans(), s0=st.sampled_from([1.0, 0.7, 2.5, 0.0]))
+def test_fuzz_three_statements_agree(tris, W, H, angles, image, s0):
+    """mode 0 (faithful scan) == mode 1 (row termination; falls back to mode 0 for non-regular triangles)
+    == the numpy restatement, including NaN/inf/denormal coordinates, 1-cell frames and odd widths."""
+    xyz = np.array(tris, np.float32)
+    rgb = (np.arange(xyz.shape[0] * 3, dtype=np.int64) * 37 % 256).astype(np.uint8).reshape(-1, 3)
+    rot = oracle.rotation(*angles)
+    c0, z0, k0 = oracle.render(xyz, rgb, s0, W, H, rot, image=image, mode=0)
+    c1, z1, k1 = oracle.render(xyz, rgb, s0, W, H, rot, image=image, mode=1)
+    assert np.array_equal(c0, c1) and np.array_equal(z0.view(np.uint32), z1.view(np.uint32))
+    assert k0["covered"] == k1["covered"] and k0["zwrites"] == k1["zwrites"]
+    c2, z2 = restate_np.render(xyz, rgb, s0, W, H, rot, image=image)
+    assert np.array_equal(c0, c2) and np.array_equal(z0.view(np.uint32), z2.view(np.uint32))
