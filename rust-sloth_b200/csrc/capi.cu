@@ -99,9 +99,9 @@ struct sloth_ctx {
     cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
 
     // queues + per-frame aux (rowmax and FrameAux are one allocation, cleared by one memset)
-    uint32_t* walk_tri = nullptr;      // k_geom3 -> k_tail queues: same stream, one set is enough
-    unsigned long long* walk_base = nullptr;
-    uint32_t* irr_tri = nullptr;
+    uint32_t* walk_tri[2] = {nullptr, nullptr};      // k_geom3 -> k_tail queues, one per frame-state set
+    unsigned long long* walk_base[2] = {nullptr, nullptr};
+    uint32_t* irr_tri[2] = {nullptr, nullptr};
     int last_set = 0;
     cudaStream_t resolve_stream = nullptr;
     cudaEvent_t ev_geom_done[2] = {nullptr, nullptr}, ev_resolved[2] = {nullptr, nullptr};
@@ -206,15 +206,15 @@ void build_params(const sloth_ctx* c, const float rot[16], FrameParams& p)
 Queues make_queues(const sloth_ctx* c, int set)
 {
     Queues q;
-    q.walk_tri = c->walk_tri;
-    q.walk_base = c->walk_base;
-    q.irr_tri = c->irr_tri;
+    q.walk_tri = c->walk_tri[set];
+    q.walk_base = c->walk_base[set];
+    q.irr_tri = c->irr_tri[set];
     q.rowmax = reinterpret_cast<uint32_t*>(c->aux_region[set]);
     q.aux = reinterpret_cast<FrameAux*>(c->aux_region[set] + c->rowmax_bytes);
     return q;
 }
 
-// Geometry half of a frame (aux clear, k_geom3, k_tail) on stream `st`, into frame-state set `set`.
+// Geometry pass of a frame (aux clear, k_geom3) on stream `st`, into frame-state set `set`.
 int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st, bool kt)
 {
     Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb};
@@ -247,17 +247,21 @@ int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t s
             if (dyn > 16384) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             kern<<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->sc_chunks, c->keys[set], q, batch_chunks, rowmax_shared);
         }
-        if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
-        {
-            const uint32_t wb = (uint32_t)c->sm_count * c->tail_blocks_per_sm, ib = std::max<uint32_t>(1u, (uint32_t)c->sm_count / 2u);
-            k_tail<<<wb + ib, 128, 0, st>>>(p, sc, c->keys[set], q, wb);
-        }
-        if (kt) CU(cudaEventRecord(c->ev[EV_WALK], st));
-        c->launches += 2;
-    } else if (kt) {
-        CU(cudaEventRecord(c->ev[EV_GEOM], st));
-        CU(cudaEventRecord(c->ev[EV_WALK], st));
+        c->launches += 1;
     }
+    if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
+    return SLOTH_OK;
+}
+
+// Follow-up pass of a frame (k_tail: queued row bands + irregular triangles) on stream `st`.
+int enqueue_tail(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
+{
+    if (!c->n_tri) return SLOTH_OK;
+    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb};
+    const Queues q = make_queues(c, set);
+    const uint32_t wb = (uint32_t)c->sm_count * c->tail_blocks_per_sm, ib = std::max<uint32_t>(1u, (uint32_t)c->sm_count / 2u);
+    k_tail<<<wb + ib, 128, 0, st>>>(p, sc, c->keys[set], q, wb);
+    c->launches += 1;
     return SLOTH_OK;
 }
 
@@ -301,6 +305,9 @@ int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z
     if (timed) CU(cudaEventRecord(c->ev[EV_START], st));
     int rc = enqueue_geometry(c, p, 0, st, kt);
     if (rc) return rc;
+    rc = enqueue_tail(c, p, 0, st);
+    if (rc) return rc;
+    if (kt) CU(cudaEventRecord(c->ev[EV_WALK], st));
     if (kt) CU(cudaEventRecord(c->ev[EV_RESOLVE_BEGIN], st));
     rc = enqueue_resolve(c, p, 0, st, d_out, d_z);
     if (rc) return rc;
@@ -312,7 +319,7 @@ int enqueue_frame(sloth_ctx* c, const float rot[16], uint32_t* d_out, float* d_z
 }
 
 // Frames k = 0..n-1 with the geometry of frame k+1 (issue-bound, stream G = c->stream) overlapping the
-// resolve of frame k (memory-bound, stream R): two frame-state sets alternate.  Frame k's cells go to
+// follow-up pass and the resolve of frame k (stream R): two frame-state sets alternate.  Frame k's cells go to
 // out(k) on the device; before_resolve(k) / after_resolve(k) run right before / after resolve k is
 // enqueued on R (used to chain the device->host copies of the host batch).  On return everything has been enqueued and G waits for the last resolves.
 template <typename BeforeFn, typename OutFn, typename AfterFn>
@@ -328,6 +335,8 @@ int enqueue_overlapped(sloth_ctx* c, const float* rots, size_t n_frames, BeforeF
         if (rc) return rc;
         CU(cudaEventRecord(c->ev_geom_done[set], c->stream));
         CU(cudaStreamWaitEvent(c->resolve_stream, c->ev_geom_done[set], 0));
+        rc = enqueue_tail(c, p, set, c->resolve_stream);   // k_tail(k) and resolve(k) run beside k_geom3(k+1)
+        if (rc) return rc;
         rc = before_resolve(k);
         if (rc) return rc;
         rc = enqueue_resolve(c, p, set, c->resolve_stream, out(k), nullptr);
@@ -429,7 +438,8 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     {
         int lo = 0, hi = 0;   // resolve kernels squeeze in beside the persistent geometry blocks: give them priority
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CU(cudaStreamCreateWithPriority(&c->resolve_stream, cudaStreamNonBlocking, hi));
+        const char* pr = std::getenv("SLOTH_RESOLVE_PRIO");   // profiling knob: 0 = lowest priority instead of highest
+        CU(cudaStreamCreateWithPriority(&c->resolve_stream, cudaStreamNonBlocking, (pr && std::atoi(pr) == 0) ? lo : hi));
     }
     for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) {
@@ -458,9 +468,7 @@ int sloth_ctx_destroy(sloth_ctx* c)
     cudaFree(c->sc_z3);
     cudaFree(c->sc_rgb);
     cudaFree(c->sc_chunks);
-    cudaFree(c->walk_tri);
-    cudaFree(c->walk_base);
-    cudaFree(c->irr_tri);
+    for (int i = 0; i < 2; ++i) { cudaFree(c->walk_tri[i]); cudaFree(c->walk_base[i]); cudaFree(c->irr_tri[i]); }
     for (int i = 0; i < EV_N; ++i) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) {
         cudaEventDestroy(c->ev_rendered[i]);
@@ -485,9 +493,11 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
     CU(cudaStreamSynchronize(c->resolve_stream));
     cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_z3); cudaFree(c->sc_rgb); cudaFree(c->sc_chunks);
     c->sc_chunks = nullptr;
-    cudaFree(c->walk_tri); cudaFree(c->walk_base); cudaFree(c->irr_tri);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->walk_tri[i]); cudaFree(c->walk_base[i]); cudaFree(c->irr_tri[i]);
+        c->walk_tri[i] = c->irr_tri[i] = nullptr; c->walk_base[i] = nullptr;
+    }
     c->sc_a = c->sc_b = nullptr; c->sc_z3 = nullptr; c->sc_rgb = nullptr;
-    c->walk_tri = c->irr_tri = nullptr; c->walk_base = nullptr;
     c->have_scene = false;
     const size_t n = n_tri ? n_tri : 1;
     CU(cudaMalloc(&c->sc_a, n * sizeof(float4)));
@@ -496,9 +506,11 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
     CU(cudaMalloc(&c->sc_rgb, n * sizeof(uint32_t)));
     const size_t n_padded = (n + 31) & ~(size_t)31;
     if (c->tma_feed) CU(cudaMalloc(&c->sc_chunks, n_padded / 32 * CHUNK_BYTES));   // second copy only for the TMA feed
-    CU(cudaMalloc(&c->walk_tri, n * sizeof(uint32_t)));
-    CU(cudaMalloc(&c->walk_base, n * sizeof(unsigned long long)));
-    CU(cudaMalloc(&c->irr_tri, n * sizeof(uint32_t)));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMalloc(&c->walk_tri[i], n * sizeof(uint32_t)));
+        CU(cudaMalloc(&c->walk_base[i], n * sizeof(unsigned long long)));
+        CU(cudaMalloc(&c->irr_tri[i], n * sizeof(uint32_t)));
+    }
     if (n_tri) {
         float* d_xyz = nullptr;
         uint8_t* d_rgb = nullptr;
