@@ -181,8 +181,10 @@ SLOTH_DEV void g3_emit(const FrameParams& p, const G3Queue& wq, uint32_t head, u
     }
 }
 
+// 72 registers: three persistent blocks per SM must leave room (8 K registers) for one block of the
+// resolve / follow-up kernels of the previous frame, which run beside this kernel on a second stream.
 template <bool CHECK_REGULAR, bool BAND, bool TMA>
-__global__ void __launch_bounds__(G3_WARPS * 32, G3_BLOCKS_PER_SM) k_geom3(const __grid_constant__ FrameParams p, const Scene sc,
+__global__ void __maxnreg__(72) k_geom3(const __grid_constant__ FrameParams p, const Scene sc,
                                                             const float* __restrict__ chunks,
                                                             unsigned long long* __restrict__ keys, const Queues q,
                                                             const uint32_t batch_chunks, const uint32_t rowmax_shared)
