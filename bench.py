@@ -69,6 +69,8 @@ class ClockSampler:
         self.index, self.lines, self.proc = index, [], None
 
     def __enter__(self):
+        if os.environ.get("BENCH_NO_CLOCKS"):   # diagnostic only
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],

@@ -80,6 +80,8 @@ struct sloth_ctx {
     uint32_t* sc_rgb = nullptr;
     float* sc_chunks = nullptr;      // TMA feed: 1280-byte chunks of 32 triangles
     uint32_t geom_blocks_per_sm = G3_BLOCKS_PER_SM;   // SLOTH_GRID overrides (profiling)
+    int carveout_override = -1;
+    int carveout_set = -1;            // shared-memory carveout (%) currently applied to the frame kernels
     uint32_t tail_blocks_per_sm = 8;  // SLOTH_TAIL overrides (profiling)
     bool tma_feed = false;           // SLOTH_TMA=1 feeds k_geom3 through cp.async.bulk + mbarrier (measured 3 % slower)
     uint32_t n_tri = 0;
@@ -245,6 +247,23 @@ int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t s
             else kern = bounded ? (band_mode ? k_geom3<false, true, false> : k_geom3<false, false, false>)
                                 : (band_mode ? k_geom3<true, true, false> : k_geom3<true, false, false>);
             if (dyn > 16384) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            {
+                // Kernels that run side by side on one SM (k_geom3 of frame k+1 with k_tail / k_resolve of frame k)
+                // must agree on the L1 / shared-memory split, or the SM has to drain before it can switch.  Ask
+                // for one carveout that holds three geometry blocks and apply it to all frame kernels.
+                const size_t per_block = sizeof(G3Queue) * G3_WARPS + dyn + 1024;
+                int pct = (int)((per_block * blocks_per_sm * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
+                pct = std::min(100, std::max(50, pct));
+                if (c->carveout_override >= 0) pct = c->carveout_override;
+                if (pct != c->carveout_set) {
+                    CU(cudaFuncSetAttribute(k_tail, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                    CU(cudaFuncSetAttribute(k_resolve_even, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                    CU(cudaFuncSetAttribute(k_resolve_odd, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                    CU(cudaFuncSetAttribute(k_clear_keys_odd, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                    c->carveout_set = pct;
+                }
+                CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+            }
             kern<<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->sc_chunks, c->keys[set], q, batch_chunks, rowmax_shared);
         }
         c->launches += 1;
@@ -431,6 +450,7 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     c->sm_count = prop.multiProcessorCount;
     if (const char* g = std::getenv("SLOTH_DEBUG")) c->debug = (uint32_t)std::atoi(g);
     if (const char* g = std::getenv("SLOTH_TMA")) c->tma_feed = std::atoi(g) != 0;
+    if (const char* g = std::getenv("SLOTH_CARVEOUT")) c->carveout_override = std::atoi(g);   // profiling knob
     if (const char* g = std::getenv("SLOTH_TAIL")) c->tail_blocks_per_sm = (uint32_t)std::max(1, std::atoi(g));
     if (const char* g = std::getenv("SLOTH_GRID")) c->geom_blocks_per_sm = (uint32_t)std::max(1, std::atoi(g));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
