@@ -88,3 +88,26 @@ def test_webify_stream_framing():
     f = [np.array([ord("@") | 7 << 8], np.uint32), np.array([ord(" ")], np.uint32)]
     s = tt.webify_stream(f)
     assert s == (b'let frames = [\n`\n<span style="color:rgb(7,0,0)">@`,\n`\n<span style="color:rgb(0,0,0)"> `];\n')
+
+
+def test_webify_framing_matches_the_reference_player_data():
+    """the -j wire format.  src-webify/data.js (a stale 100-frame export shipped with the
+    reference; its spans are run-length merged, so only the framing is comparable) and our stream use the same
+    tokens: `let frames = [`, a back-tick line before every frame, "`," after it, "`];" after the last."""
+    import re
+    import rust_sloth_b200  # noqa: F401
+    from rust_sloth_b200 import turntable as tt
+    cells = np.full(10 * 4 + 4, ord(" "), np.uint32)
+    cells[1::10][:4] = ord("\n")
+    ours = tt.webify_stream([cells] * 3).decode()
+    assert ours.startswith("let frames = [\n`\n<span") and ours.endswith("`];\n")
+    assert len(re.findall(r"(?m)^`$", ours)) == 3 and ours.count("`,\n") == 2
+    path = "/root/reference/src-webify/data.js"
+    if os.path.exists(path):
+        ref = open(path).read()
+        assert ref.startswith("let frames = [\n`\n<span") and ref.endswith("`];\n")
+        n = len(re.findall(r"(?m)^`$", ref))
+        assert n == 100 and ref.count("`,\n") == n - 1
+        # render.js only needs `frames` to be an array of strings: same JS shape on both sides
+        assert re.fullmatch(r"let frames = \[\n(`\n[^`]*`,\n)*`\n[^`]*`\];\n", ours)
+        assert re.fullmatch(r"let frames = \[\n(`\n[^`]*`,\n)*`\n[^`]*`\];\n", ref)
