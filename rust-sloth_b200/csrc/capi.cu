@@ -465,7 +465,11 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     for (int i = 0; i < 2; ++i) {
         CU(cudaEventCreateWithFlags(&c->ev_rendered[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&c->ev_geom_done[i], cudaEventDisableTiming));
+        // A timing event on purpose.  Recording it costs the geometry stream ~2 us after k_geom3(k), which is
+        // what lets k_tail(k) / resolve(k) reach the SMs ahead of k_geom3(k+1); with a cudaEventDisableTiming
+        // event about half of the B200s measured ran the overlapped batch at 185 us/frame instead of 162
+        // (profiles/README.md, "overlap variance").
+        CU(cudaEventCreateWithFlags(&c->ev_geom_done[i], cudaEventDefault));
         CU(cudaEventCreateWithFlags(&c->ev_resolved[i], cudaEventDisableTiming));
     }
     *out = c;
