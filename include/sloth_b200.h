@@ -43,7 +43,10 @@ enum {
     SLOTH_E_ARG = -1,      /* bad argument (null pointer, zero size, out of range) */
     SLOTH_E_CUDA = -2,     /* CUDA runtime error / no usable device */
     SLOTH_E_STATE = -3,    /* call order (render before scene_set / resize) */
-    SLOTH_E_TOO_LARGE = -4 /* more than 2^27-1 triangles, or W*H+H >= 2^31, or W/H > 65535 */
+    SLOTH_E_TOO_LARGE = -4, /* more than 2^27-1 triangles, or W*H+H >= 2^31, or W/H > 65535 */
+    SLOTH_E_IO = -5,        /* a model or material file could not be read */
+    SLOTH_E_PARSE = -6,     /* malformed model file (message in the reference's wording) */
+    SLOTH_E_UNSUPPORTED = -7 /* well-formed input the device parser does not decide (inf/nan, >19 digits on a rounding boundary ...) */
 };
 
 typedef struct sloth_ctx sloth_ctx;
@@ -63,6 +66,31 @@ SLOTH_API int sloth_ctx_destroy(sloth_ctx *ctx);
  */
 SLOTH_API int sloth_scene_set(sloth_ctx *ctx, const float *xyz, const uint8_t *rgb, size_t n_tri,
                               float scene_max);
+
+/*
+ * Model loading on the device: match_meshes (inputs.rs:95-129: tobj 3.2.2 / stl_io 0.4.2) and
+ * to_meshes (geometry.rs:83-189: de-indexed soup, fan triangulation, colour rules, bounding boxes) for files of
+ * any size.  The file's bytes go to the GPU once; line splitting, decimal -> f32 conversion (correctly rounded,
+ * like Rust's f32::from_str), index resolution, triangulation, colours and the max-coordinate fold of
+ * Context::update (context.rs:106-113) all run there and the soup never visits the host.
+ *
+ *   sloth_scene_load   the whole of match_meshes for one CLI value ("a.obj b.stl", split on ' ', extension
+ *                      dispatch, .mtl files resolved next to the .obj); replaces the scene like sloth_scene_set.
+ *   sloth_loader_*     the same for bytes the caller already holds: begin, add files in draw order, commit.
+ *                      `mtl_dir` is the directory (with trailing '/', or "" / NULL for the cwd) where mtllib
+ *                      statements are looked up.  Texts must be shorter than 4 GiB each.
+ *   sloth_scene_size / sloth_scene_get   read the resident soup back (tests, tools).
+ * Errors carry the reference's wording (SLOTH_E_PARSE / SLOTH_E_IO).  SLOTH_E_UNSUPPORTED marks input that is
+ * legal but outside what the device parser decides exactly; nothing is loaded then and the caller may parse on
+ * the host and use sloth_scene_set (the `sloth` CLI does, with a note on stderr).
+ */
+SLOTH_API int sloth_scene_load(sloth_ctx *ctx, const char *models_arg, size_t *n_tri_out, float *scene_max_out);
+SLOTH_API int sloth_loader_begin(sloth_ctx *ctx);
+SLOTH_API int sloth_loader_add_obj(sloth_ctx *ctx, const char *text, size_t len, const char *mtl_dir);
+SLOTH_API int sloth_loader_add_stl(sloth_ctx *ctx, const void *bytes, size_t len);
+SLOTH_API int sloth_loader_commit(sloth_ctx *ctx, size_t *n_tri_out, float *scene_max_out);
+SLOTH_API size_t sloth_scene_size(const sloth_ctx *ctx);
+SLOTH_API int sloth_scene_get(sloth_ctx *ctx, float *xyz, uint8_t *rgb, float *scene_max_out);
 
 /* match_dimensions (inputs.rs:159-169) / the size adoption in Context::update
  * (context.rs:134-137).  (Re)allocates the frame state for W x H cells. */
@@ -145,6 +173,8 @@ typedef struct sloth_stats {
     uint32_t stamp_fixups;     /* last frame: newline-vs-wrapped-fragment order fix-ups */
     float last_frame_ms;       /* device time of the last sloth_render / per frame of the last batch */
     float geom_ms, walk_ms, resolve_ms; /* per-kernel device times of the last sloth_render when timing is on */
+    float load_read_ms, load_parse_ms, load_commit_ms; /* last sloth_scene_load: file -> pinned memory, copy + device
+                                                          parse, soup -> resident scene (host wall clock) */
 } sloth_stats;
 
 SLOTH_API int sloth_stats_get(sloth_ctx *ctx, sloth_stats *out);

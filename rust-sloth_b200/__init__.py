@@ -39,6 +39,7 @@ LIB_PATH = os.path.join(_HERE, "libsloth_b200.so")
 HOST_LIB_PATH = os.path.join(_HERE, "libsloth_host.so")
 
 SLOTH_OK, SLOTH_E_ARG, SLOTH_E_CUDA, SLOTH_E_STATE, SLOTH_E_TOO_LARGE = 0, -1, -2, -3, -4
+SLOTH_E_IO, SLOTH_E_PARSE, SLOTH_E_UNSUPPORTED = -5, -6, -7
 
 # every symbol include/sloth_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -48,6 +49,8 @@ ABI_SYMBOLS = [
     "sloth_rotation_from_euler", "sloth_utransform", "sloth_turntable_pitches", "sloth_cells_per_frame",
     "sloth_pinned_alloc", "sloth_pinned_free", "sloth_ctx_stream", "sloth_render_device_batch",
     "sloth_text_capacity", "sloth_render_text", "sloth_render_text_batch", "sloth_flush_device",
+    "sloth_scene_load", "sloth_loader_begin", "sloth_loader_add_obj", "sloth_loader_add_stl", "sloth_loader_commit",
+    "sloth_scene_size", "sloth_scene_get",
 ]
 
 
@@ -64,6 +67,7 @@ class Stats(C.Structure):
         ("irregular_tris", C.c_uint32), ("stamp_fixups", C.c_uint32),
         ("last_frame_ms", C.c_float), ("geom_ms", C.c_float), ("walk_ms", C.c_float),
         ("resolve_ms", C.c_float),
+        ("load_read_ms", C.c_float), ("load_parse_ms", C.c_float), ("load_commit_ms", C.c_float),
     ]
 
     def as_dict(self) -> dict:
@@ -115,6 +119,14 @@ def load_library() -> C.CDLL:
     L.sloth_cells_per_frame.restype = C.c_size_t
     L.sloth_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.sloth_pinned_free.argtypes = [vp]
+    L.sloth_scene_load.argtypes = [vp, C.c_char_p, C.POINTER(C.c_size_t), fp]
+    L.sloth_loader_begin.argtypes = [vp]
+    L.sloth_loader_add_obj.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p]
+    L.sloth_loader_add_stl.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.sloth_loader_commit.argtypes = [vp, C.POINTER(C.c_size_t), fp]
+    L.sloth_scene_size.argtypes = [vp]
+    L.sloth_scene_size.restype = C.c_size_t
+    L.sloth_scene_get.argtypes = [vp, fp, C.POINTER(C.c_uint8), fp]
     _lib = L
     return L
 
@@ -309,6 +321,42 @@ class Context:
                                        xyz.shape[0], np.float32(scene_max)))
         self._scene_max = np.float32(scene_max)
         self.n_tri = xyz.shape[0]
+
+    # -- device loaders (inputs.rs:95-129 + geometry.rs:83-189 on the GPU) ----------------
+    def _loaded(self, n: C.c_size_t, m: C.c_float) -> tuple[int, np.float32]:
+        self.n_tri = int(n.value)
+        self._scene_max = np.float32(m.value)
+        return self.n_tri, self._scene_max
+
+    def load_models(self, arg: str) -> tuple[int, np.float32]:
+        """match_meshes for one CLI value, parsed on the device; returns (triangles, scene_max)."""
+        n, m = C.c_size_t(0), C.c_float(0.0)
+        _check(self._L.sloth_scene_load(self._h, arg.encode(), C.byref(n), C.byref(m)))
+        return self._loaded(n, m)
+
+    def load_bytes(self, files) -> tuple[int, np.float32]:
+        """files: iterable of ("obj", text_bytes, mtl_dir) / ("stl", bytes); draw order = list order."""
+        _check(self._L.sloth_loader_begin(self._h))
+        for f in files:
+            if f[0] == "obj":
+                mtl_dir = f[2] if len(f) > 2 and f[2] is not None else ""
+                _check(self._L.sloth_loader_add_obj(self._h, f[1], len(f[1]), mtl_dir.encode()))
+            elif f[0] == "stl":
+                _check(self._L.sloth_loader_add_stl(self._h, f[1], len(f[1])))
+            else:
+                raise ValueError(f"unknown model kind {f[0]!r}")
+        n, m = C.c_size_t(0), C.c_float(0.0)
+        _check(self._L.sloth_loader_commit(self._h, C.byref(n), C.byref(m)))
+        return self._loaded(n, m)
+
+    def scene(self) -> tuple[np.ndarray, np.ndarray, np.float32]:
+        """The resident soup read back from the device: (xyz [n,9] f32, rgb [n,3] u8, scene_max)."""
+        n = int(self._L.sloth_scene_size(self._h))
+        xyz = np.empty((n, 9), np.float32)
+        rgb = np.empty((n, 3), np.uint8)
+        m = C.c_float(0.0)
+        _check(self._L.sloth_scene_get(self._h, _fp(xyz), rgb.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(m)))
+        return xyz, rgb, np.float32(m.value)
 
     def resize(self, width: int, height: int) -> None:
         _check(self._L.sloth_ctx_resize(self._h, int(width), int(height)))

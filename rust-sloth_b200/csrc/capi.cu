@@ -20,6 +20,7 @@
 #include "../../include/sloth_b200.h"
 #include "kernels.cuh"
 #include "flush.cuh"
+#include "loader.cuh"
 
 using namespace sloth;
 
@@ -132,6 +133,9 @@ struct sloth_ctx {
     size_t batch_frames = 0;
     bool batch_pending = false;      // device batch enqueued, its time not yet read
     bool last_was_batch = false;
+
+    float load_ms[3] = {0.f, 0.f, 0.f};      // last sloth_scene_load: read, parse, commit
+    struct LoaderState* loader = nullptr;   // staged soup segments of sloth_loader_* (loader_api.inl)
 };
 
 namespace {
@@ -422,7 +426,51 @@ int check_ready(sloth_ctx* c)
     return SLOTH_OK;
 }
 
+// Drop the resident scene and allocate room for n_tri triangles (plus the per-scene queues).
+int alloc_scene(sloth_ctx* c, size_t n_tri)
+{
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->resolve_stream));
+    cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_z3); cudaFree(c->sc_rgb); cudaFree(c->sc_chunks);
+    c->sc_chunks = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->walk_tri[i]); cudaFree(c->walk_base[i]); cudaFree(c->irr_tri[i]);
+        c->walk_tri[i] = c->irr_tri[i] = nullptr; c->walk_base[i] = nullptr;
+    }
+    c->sc_a = c->sc_b = nullptr; c->sc_z3 = nullptr; c->sc_rgb = nullptr;
+    c->have_scene = false;
+    c->n_tri = 0;
+    const size_t n = n_tri ? n_tri : 1;
+    CU(cudaMalloc(&c->sc_a, n * sizeof(float4)));
+    CU(cudaMalloc(&c->sc_b, n * sizeof(float4)));
+    CU(cudaMalloc(&c->sc_z3, n * sizeof(float)));
+    CU(cudaMalloc(&c->sc_rgb, n * sizeof(uint32_t)));
+    const size_t n_padded = (n + 31) & ~(size_t)31;
+    if (c->tma_feed) CU(cudaMalloc(&c->sc_chunks, n_padded / 32 * CHUNK_BYTES));   // second copy only for the TMA feed
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMalloc(&c->walk_tri[i], n * sizeof(uint32_t)));
+        CU(cudaMalloc(&c->walk_base[i], n * sizeof(unsigned long long)));
+        CU(cudaMalloc(&c->irr_tri[i], n * sizeof(uint32_t)));
+    }
+    return SLOTH_OK;
+}
+
+// After sc_a/sc_b/sc_z3/sc_rgb have been filled on c->stream: derived copies, then wait.
+int finish_scene(sloth_ctx* c, size_t n_tri)
+{
+    if (c->tma_feed && n_tri) {
+        const size_t n_padded = (n_tri + 31) & ~(size_t)31;
+        k_pack_chunks<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(c->sc_a, c->sc_b, c->sc_z3, (uint32_t)n_tri, (uint32_t)n_padded, c->sc_chunks);
+        c->launches += 1;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return SLOTH_OK;
+}
+
 }  // namespace
+
+#include "loader_api.inl"
 
 extern "C" {
 
@@ -500,6 +548,10 @@ int sloth_ctx_destroy(sloth_ctx* c)
         cudaEventDestroy(c->ev_geom_done[i]);
         cudaEventDestroy(c->ev_resolved[i]);
     }
+    if (c->loader) {
+        c->loader->clear();
+        delete c->loader;
+    }
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->resolve_stream);
@@ -513,28 +565,8 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
     if (n_tri && (!xyz || !rgb)) return fail(SLOTH_E_ARG, "xyz/rgb is null");
     if (n_tri > MAX_TRIS) return fail(SLOTH_E_TOO_LARGE, "%zu triangles; the depth key holds a 27-bit index (max %u)", n_tri, MAX_TRIS);
     CU(cudaSetDevice(c->device));
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaStreamSynchronize(c->resolve_stream));
-    cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_z3); cudaFree(c->sc_rgb); cudaFree(c->sc_chunks);
-    c->sc_chunks = nullptr;
-    for (int i = 0; i < 2; ++i) {
-        cudaFree(c->walk_tri[i]); cudaFree(c->walk_base[i]); cudaFree(c->irr_tri[i]);
-        c->walk_tri[i] = c->irr_tri[i] = nullptr; c->walk_base[i] = nullptr;
-    }
-    c->sc_a = c->sc_b = nullptr; c->sc_z3 = nullptr; c->sc_rgb = nullptr;
-    c->have_scene = false;
-    const size_t n = n_tri ? n_tri : 1;
-    CU(cudaMalloc(&c->sc_a, n * sizeof(float4)));
-    CU(cudaMalloc(&c->sc_b, n * sizeof(float4)));
-    CU(cudaMalloc(&c->sc_z3, n * sizeof(float)));
-    CU(cudaMalloc(&c->sc_rgb, n * sizeof(uint32_t)));
-    const size_t n_padded = (n + 31) & ~(size_t)31;
-    if (c->tma_feed) CU(cudaMalloc(&c->sc_chunks, n_padded / 32 * CHUNK_BYTES));   // second copy only for the TMA feed
-    for (int i = 0; i < 2; ++i) {
-        CU(cudaMalloc(&c->walk_tri[i], n * sizeof(uint32_t)));
-        CU(cudaMalloc(&c->walk_base[i], n * sizeof(unsigned long long)));
-        CU(cudaMalloc(&c->irr_tri[i], n * sizeof(uint32_t)));
-    }
+    int rc = alloc_scene(c, n_tri);
+    if (rc) return rc;
     if (n_tri) {
         float* d_xyz = nullptr;
         uint8_t* d_rgb = nullptr;
@@ -543,13 +575,11 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
         CU(cudaMemcpyAsync(d_xyz, xyz, n_tri * 9 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(d_rgb, rgb, n_tri * 3, cudaMemcpyHostToDevice, c->stream));
         k_pack_scene<<<(unsigned)((n_tri + 255) / 256), 256, 0, c->stream>>>(d_xyz, d_rgb, (uint32_t)n_tri, c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb);
-        if (c->tma_feed)
-            k_pack_chunks<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(c->sc_a, c->sc_b, c->sc_z3, (uint32_t)n_tri, (uint32_t)n_padded, c->sc_chunks);
-        c->launches += c->tma_feed ? 2 : 1;
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(c->stream));
+        c->launches += 1;
+        rc = finish_scene(c, n_tri);
         cudaFree(d_xyz);
         cudaFree(d_rgb);
+        if (rc) return rc;
     }
     {   // finite and |v| <= 2^20 everywhere?  (NaN fails the comparison)
         bool clean = true;
@@ -818,6 +848,9 @@ int sloth_stats_get(sloth_ctx* c, sloth_stats* out)
     out->frames = c->frames;
     out->kernel_launches = c->launches;
     out->n_tri = c->n_tri;
+    out->load_read_ms = c->load_ms[0];
+    out->load_parse_ms = c->load_ms[1];
+    out->load_commit_ms = c->load_ms[2];
     if (c->sized && c->aux_region[c->last_set]) {
         FrameAux aux;
         CU(cudaMemcpy(&aux, c->aux_region[c->last_set] + c->rowmax_bytes, sizeof aux, cudaMemcpyDeviceToHost));

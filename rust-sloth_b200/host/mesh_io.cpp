@@ -59,35 +59,21 @@ bool parse_floatn(const std::vector<std::string>& w, size_t& pos, std::vector<fl
     return got == n;
 }
 
-// Rust `f32 as u8`: truncate toward zero, saturate, NaN -> 0 (geometry.rs:111-124).
-uint8_t f32_as_u8(float v)
-{
-    if (!(v > 0.0f)) return 0;
-    if (v >= 255.0f) return 255;
-    return (uint8_t)v;
-}
-
 void dirname_of(const std::string& path, std::string& dir)
 {
     size_t p = path.find_last_of('/');
     dir = (p == std::string::npos) ? std::string() : path.substr(0, p + 1);
 }
 
-struct Material {
-    std::string name;
-    float diffuse[3] = {0.f, 0.f, 0.f};
-};
+using Material = MtlMaterial;
 
-bool load_mtl(const std::string& path, std::vector<Material>& mats, std::map<std::string, size_t>& mat_map,
-              std::string& err)
+bool load_mtl_entries(const std::string& path, std::vector<Material>& loaded, std::string& err)
 {
     std::ifstream in(path);
     if (!in) {
         err = "open failed: " + path;
         return false;
     }
-    const size_t offset = mats.size();
-    std::vector<Material> loaded;
     std::string line;
     bool have = false;
     Material cur;
@@ -111,6 +97,15 @@ bool load_mtl(const std::string& path, std::vector<Material>& mats, std::map<std
         }
     }
     if (have) loaded.push_back(cur);
+    return true;
+}
+
+bool load_mtl(const std::string& path, std::vector<Material>& mats, std::map<std::string, size_t>& mat_map,
+              std::string& err)
+{
+    const size_t offset = mats.size();
+    std::vector<Material> loaded;
+    if (!load_mtl_entries(path, loaded, err)) return false;
     for (size_t i = 0; i < loaded.size(); ++i) {
         mat_map[loaded[i].name] = offset + i;
         mats.push_back(loaded[i]);
@@ -189,6 +184,21 @@ bool export_model(const ObjState& st, const std::vector<Material>& mats, bool ha
 }
 
 }  // namespace
+
+uint8_t f32_as_u8(float v)
+{
+    if (!(v > 0.0f)) return 0;
+    if (v >= 255.0f) return 255;
+    return (uint8_t)v;
+}
+
+bool load_mtl_file(const std::string& path, std::vector<MtlMaterial>& out, std::string& err)
+{
+    std::vector<MtlMaterial> loaded;
+    if (!load_mtl_entries(path, loaded, err)) return false;
+    out.insert(out.end(), loaded.begin(), loaded.end());
+    return true;
+}
 
 bool load_obj(const std::string& path, std::vector<SimpleMesh>& out, std::string& err)
 {

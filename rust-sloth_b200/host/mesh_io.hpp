@@ -25,6 +25,16 @@ struct SimpleMesh {
     size_t size() const { return xyz.size() / 9; }
 };
 
+// One `newmtl` block of a .mtl file (tobj Material: only the name and Kd are used, geometry.rs:109-115).
+struct MtlMaterial {
+    std::string name;
+    float diffuse[3] = {0.f, 0.f, 0.f};
+};
+// Appends the materials of one .mtl file in file order.  false + err when the file cannot be read or a Kd is bad.
+bool load_mtl_file(const std::string& path, std::vector<MtlMaterial>& out, std::string& err);
+// Rust `f32 as u8`: truncate toward zero, saturate, NaN -> 0 (geometry.rs:111-124).
+uint8_t f32_as_u8(float v);
+
 // match_meshes(): `arg` is the single CLI value, split on ' '.  On failure
 // returns false and sets `err` to the reference's message format
 // ("filename: [..] couldn't load, ..").

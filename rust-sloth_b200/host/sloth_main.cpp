@@ -147,11 +147,28 @@ int main(int argc, char** argv)
     if (sub.present && !sub.values.count("width"))
         usage_error("The following required arguments were not provided:\n    -w <width>");
 
-    std::vector<sloth::SimpleMesh> meshes;
+    // match_meshes (main.rs:31) on the device: the files are parsed by sloth_scene_load and the soup never
+    // visits the host.  Input that is legal but outside the device parser's grammar is parsed here instead.
+    sloth_ctx* ctx = nullptr;
+    check(sloth_ctx_create(0, sub.present ? 1 : 0, &ctx));
     std::string err;
-    if (!sloth::match_meshes(top.values["input"], meshes, err)) {
-        std::fprintf(stderr, "Error: \"%s\"\n", err.c_str());
-        return 1;
+    {
+        const int rc = sloth_scene_load(ctx, top.values["input"].c_str(), nullptr, nullptr);
+        if (rc == SLOTH_E_UNSUPPORTED) {
+            std::fprintf(stderr, "note: %s -- parsing on the host\n", sloth_last_error());
+            std::vector<sloth::SimpleMesh> meshes;
+            if (!sloth::match_meshes(top.values["input"], meshes, err)) {
+                std::fprintf(stderr, "Error: \"%s\"\n", err.c_str());
+                return 1;
+            }
+            std::vector<float> xyz;
+            std::vector<uint8_t> rgb;
+            sloth::flatten(meshes, xyz, rgb);
+            check(sloth_scene_set(ctx, xyz.data(), rgb.data(), rgb.size() / 3, sloth::scene_scale0(meshes)));
+        } else if (rc != SLOTH_OK) {
+            std::fprintf(stderr, "Error: \"%s\"\n", sloth_last_error());
+            return 1;
+        }
     }
     float turntable[4];
     if (!match_turntable(top, turntable, err)) { std::fprintf(stderr, "Error: %s\n", err.c_str()); return 1; }
@@ -177,13 +194,6 @@ int main(int argc, char** argv)
             webify = true;
         }
     }
-
-    std::vector<float> xyz;
-    std::vector<uint8_t> rgb;
-    sloth::flatten(meshes, xyz, rgb);
-    sloth_ctx* ctx = nullptr;
-    check(sloth_ctx_create(0, image ? 1 : 0, &ctx));
-    check(sloth_scene_set(ctx, xyz.data(), rgb.data(), rgb.size() / 3, sloth::scene_scale0(meshes)));
 
     if (image) {
         check(sloth_ctx_resize(ctx, W, H));
