@@ -93,6 +93,9 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
+    def samples_since(self, t0):
+        return sum(1 for t, line in list(self.lines) if t >= t0 and line.count(",") >= 8)
+
     def summary(self, t0, t1):
         sm, mx, reasons = [], [], set()
         for t, line in self.lines:
@@ -224,21 +227,22 @@ def run_b200(args, rank, local_rank, world):
     # (issue-bound) overlaps the resolve of frame k (memory-bound) on a second stream.
     warm_rots = np.stack([rots[f] for f in my_frames[:Wm]])
     timed_rots = np.stack([rots[f] for f in my_frames[Wm:]])
-    ctx.render_device_batch(warm_rots, d_cells.data_ptr(), 0)
-    ctx.sync()
-    barrier()
-    launches0 = ctx.stats()["kernel_launches"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank) as clk:   # started before the warm-up: nvidia-smi needs a moment to come up
+        ctx.render_device_batch(warm_rots, d_cells.data_ptr(), 0)
+        ctx.sync()
+        barrier()
+        launches0 = ctx.stats()["kernel_launches"]
         t_wall0 = time.time()
         ev0.record(stream)
         ctx.render_device_batch(timed_rots, d_cells.data_ptr(), 0)
         ev1.record(stream)
         ctx.sync()
         launches_timed = ctx.stats()["kernel_launches"] - launches0   # kernels of this library, counted at launch
-        # keep the GPU in the same state a little longer so the 100 ms sampler sees the load
+        # keep the GPU in the same state a little longer so the 100 ms sampler sees the load (until it has
+        # delivered a few samples: with 8 ranks starting nvidia-smi at once the first line can take a second)
         t_busy = time.time()
-        while time.time() - t_busy < 0.5:
+        while time.time() - t_busy < 0.5 or (clk.proc and clk.samples_since(t_wall0) < 3 and time.time() - t_busy < 6.0):
             ctx.render_device_batch(timed_rots[:8], d_cells.data_ptr(), 0)
             ctx.sync()
         t_wall1 = time.time()
