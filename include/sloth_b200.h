@@ -173,6 +173,7 @@ typedef struct sloth_stats {
     uint32_t stamp_fixups;     /* last frame: newline-vs-wrapped-fragment order fix-ups */
     float last_frame_ms;       /* device time of the last sloth_render / per frame of the last batch */
     float geom_ms, walk_ms, resolve_ms; /* per-kernel device times of the last sloth_render when timing is on */
+    uint32_t chunks_processed; /* last frame: chunks of 32 triangles the geometry kernel did not band-cull; needs count_fragments */
     float load_read_ms, load_parse_ms, load_commit_ms; /* last sloth_scene_load: file -> pinned memory, copy + device
                                                           parse, soup -> resident scene (host wall clock) */
 } sloth_stats;

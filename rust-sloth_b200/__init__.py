@@ -67,6 +67,7 @@ class Stats(C.Structure):
         ("irregular_tris", C.c_uint32), ("stamp_fixups", C.c_uint32),
         ("last_frame_ms", C.c_float), ("geom_ms", C.c_float), ("walk_ms", C.c_float),
         ("resolve_ms", C.c_float),
+        ("chunks_processed", C.c_uint32),
         ("load_read_ms", C.c_float), ("load_parse_ms", C.c_float), ("load_commit_ms", C.c_float),
     ]
 

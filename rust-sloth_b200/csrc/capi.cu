@@ -80,6 +80,8 @@ struct sloth_ctx {
     float* sc_z3 = nullptr;
     uint32_t* sc_rgb = nullptr;
     float* sc_chunks = nullptr;      // TMA feed: 1280-byte chunks of 32 triangles
+    float4* sc_bounds = nullptr;     // bounding sphere per chunk of 32 triangles (band cull)
+    float scene_absmax = 0.0f;       // largest |coordinate| of the scene
     uint32_t geom_blocks_per_sm = G3_BLOCKS_PER_SM;   // SLOTH_GRID overrides (profiling)
     int carveout_override = -1;
     int carveout_set = -1;            // shared-memory carveout (%) currently applied to the frame kernels
@@ -207,6 +209,22 @@ void build_params(const sloth_ctx* c, const float rot[16], FrameParams& p)
     p.image = c->image ? 1u : 0u;
     p.count_frags = (c->stat_flags & 1u) ? 1u : 0u;
     p.debug = c->debug;
+    // band cull (k_geom3): |row 1 of M| rounded up, and a bound on the rounding error of any computed y' -- four
+    // roundings of terms that are at most (|m4|+|m5|+|m6|) * absmax + |m7| in magnitude, counted twice (vertex and
+    // sphere centre) with a factor 4 to spare.  Only for scenes whose coordinates are all finite and <= 2^20.
+    p.cull_on = 0u;
+    p.cull_scale = p.cull_pad = 0.0f;
+    if (band && c->scene_clean && !(c->debug & 4u)) {
+        const double m4 = p.m[4], m5 = p.m[5], m6 = p.m[6], m7 = p.m[7];
+        const double norm = std::sqrt(m4 * m4 + m5 * m5 + m6 * m6) * 1.0001;
+        const double mag = (std::fabs(m4) + std::fabs(m5) + std::fabs(m6)) * (double)c->scene_absmax + std::fabs(m7);
+        const double pad = mag * std::ldexp(1.0, -19) + 1.0e-3;
+        if (std::isfinite(norm) && std::isfinite(pad) && pad < 1.0e6) {
+            p.cull_on = 1u;
+            p.cull_scale = (float)norm;
+            p.cull_pad = (float)(pad * 1.0001);
+        }
+    }
 }
 
 Queues make_queues(const sloth_ctx* c, int set)
@@ -223,7 +241,7 @@ Queues make_queues(const sloth_ctx* c, int set)
 // Geometry pass of a frame (aux clear, k_geom3) on stream `st`, into frame-state set `set`.
 int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st, bool kt)
 {
-    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb};
+    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb, c->sc_bounds};
     const Queues q = make_queues(c, set);
     CU(cudaMemsetAsync(c->aux_region[set], 0, c->aux_bytes, st));
     if (c->n_tri) {
@@ -280,7 +298,7 @@ int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t s
 int enqueue_tail(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
 {
     if (!c->n_tri) return SLOTH_OK;
-    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb};
+    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb, c->sc_bounds};
     const Queues q = make_queues(c, set);
     const uint32_t wb = (uint32_t)c->sm_count * c->tail_blocks_per_sm, ib = std::max<uint32_t>(1u, (uint32_t)c->sm_count / 2u);
     k_tail<<<wb + ib, 128, 0, st>>>(p, sc, c->keys[set], q, wb);
@@ -291,7 +309,7 @@ int enqueue_tail(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
 // Resolve half of a frame (optional z plane, key plane -> cells, key plane reset) on stream `st`.
 int enqueue_resolve(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st, uint32_t* d_out, float* d_z)
 {
-    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb};
+    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb, c->sc_bounds};
     const Queues q = make_queues(c, set);
     const bool band = c->row1 != 0;
     const uint32_t rows = p.row1 - p.row0;
@@ -431,8 +449,9 @@ int alloc_scene(sloth_ctx* c, size_t n_tri)
 {
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->resolve_stream));
-    cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_z3); cudaFree(c->sc_rgb); cudaFree(c->sc_chunks);
+    cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_z3); cudaFree(c->sc_rgb); cudaFree(c->sc_chunks); cudaFree(c->sc_bounds);
     c->sc_chunks = nullptr;
+    c->sc_bounds = nullptr;
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->walk_tri[i]); cudaFree(c->walk_base[i]); cudaFree(c->irr_tri[i]);
         c->walk_tri[i] = c->irr_tri[i] = nullptr; c->walk_base[i] = nullptr;
@@ -447,6 +466,7 @@ int alloc_scene(sloth_ctx* c, size_t n_tri)
     CU(cudaMalloc(&c->sc_rgb, n * sizeof(uint32_t)));
     const size_t n_padded = (n + 31) & ~(size_t)31;
     if (c->tma_feed) CU(cudaMalloc(&c->sc_chunks, n_padded / 32 * CHUNK_BYTES));   // second copy only for the TMA feed
+    CU(cudaMalloc(&c->sc_bounds, (n_padded / 32 + 1) * sizeof(float4)));
     for (int i = 0; i < 2; ++i) {
         CU(cudaMalloc(&c->walk_tri[i], n * sizeof(uint32_t)));
         CU(cudaMalloc(&c->walk_base[i], n * sizeof(unsigned long long)));
@@ -462,6 +482,15 @@ int finish_scene(sloth_ctx* c, size_t n_tri)
         const size_t n_padded = (n_tri + 31) & ~(size_t)31;
         k_pack_chunks<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(c->sc_a, c->sc_b, c->sc_z3, (uint32_t)n_tri, (uint32_t)n_padded, c->sc_chunks);
         c->launches += 1;
+    }
+    c->scene_absmax = 0.0f;
+    if (n_tri) {
+        uint32_t* d_absmax = reinterpret_cast<uint32_t*>(c->sc_bounds + ((n_tri + 31) / 32));   // spare slot after the last sphere
+        CU(cudaMemsetAsync(d_absmax, 0, sizeof(uint32_t), c->stream));
+        const unsigned n_chunks = (unsigned)((n_tri + 31) / 32);
+        k_chunk_bounds<<<(n_chunks + 127) / 128, 128, 0, c->stream>>>(c->sc_a, c->sc_b, c->sc_z3, (uint32_t)n_tri, c->sc_bounds, d_absmax);
+        c->launches += 1;
+        CU(cudaMemcpyAsync(&c->scene_absmax, d_absmax, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
@@ -859,6 +888,7 @@ int sloth_stats_get(sloth_ctx* c, sloth_stats* out)
         out->walk_items = (uint32_t)(aux.walk_counter & ITEM_MASK);
         out->irregular_tris = aux.irr_count;
         out->stamp_fixups = aux.stamp_exact;
+        out->chunks_processed = aux.chunks_done;
     }
     if (c->ev_valid) {
         if (c->last_was_batch && c->batch_pending) {

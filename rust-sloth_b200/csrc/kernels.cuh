@@ -24,7 +24,8 @@ struct FrameAux {
     unsigned long long frag_counter;   // covered fragments (only when count_frags)
     uint32_t irr_count;
     uint32_t stamp_exact;              // newline-vs-wrapped-fragment order decided by the exact check
-    uint32_t pad[10];
+    uint32_t chunks_done;              // chunks of 32 triangles k_geom3 processed, i.e. not band-culled (only when count_frags)
+    uint32_t pad[9];
 };
 
 struct Queues {
@@ -196,6 +197,7 @@ __global__ void __maxnreg__(72) k_geom3(const __grid_constant__ FrameParams p, c
     const uint32_t n_warps = gridDim.x * G3_WARPS;
     const uint32_t gw = blockIdx.x * G3_WARPS + warp;
     uint32_t q_head = 0, q_count = 0, nfrag_count = 0;   // warp-uniform ring state
+    uint32_t chunks_done = 0;
     const bool do_stamps = p.image && !(p.debug & 2u);
     // Row stamps: per-block copy of rowmax in shared memory (every warp in flight stamps the same
     // few rows, and same-address traffic serialises in L2); flushed once at the end.  Frames taller
@@ -221,6 +223,25 @@ __global__ void __maxnreg__(72) k_geom3(const __grid_constant__ FrameParams p, c
     auto advance = [&](uint32_t& idx, uint32_t& pos) {
         if (++pos == batch_chunks) { pos = 0; idx += batch_jump; } else ++idx;
     };
+    // Band contexts skip a chunk when no vertex of it can have a destination row inside the band: every computed
+    // y' lies within |row 1 of M| * radius + cull_pad of the computed y' of the sphere centre, rows of a triangle
+    // are ceil()s of its y' range and a wrapped fragment lands one row further down (hence the 2).  Non-finite
+    // bounds compare false and are processed.
+    auto culled = [&](uint32_t idx) -> bool {
+        if (!BAND || TMA || !p.cull_on) return false;
+        const float4 s = __ldg(sc.bounds + idx);
+        const float yc = xform_row(p.m + 4, s.x, s.y, s.z);
+        const float R = add(mul(s.w, p.cull_scale), p.cull_pad);
+        return sub(yc, R) >= (float)p.row1 || add(add(yc, R), 2.0f) <= (float)p.krow0;
+    };
+    auto advance_live = [&](uint32_t& idx, uint32_t& pos) {   // next chunk of this warp that is not culled
+        do advance(idx, pos); while (BAND && !TMA && idx < n_chunks && culled(idx));
+    };
+    if (BAND && !TMA) {
+        while (c < n_chunks && culled(c)) advance(c, c_pos);
+        pf = c;
+        pf_pos = c_pos;
+    }
     TmaRing& ring = rings[TMA ? warp : 0];
     float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
     float C = 0.f;
@@ -231,12 +252,14 @@ __global__ void __maxnreg__(72) k_geom3(const __grid_constant__ FrameParams p, c
         }
     } else {
         if (c < n_chunks && c * 32u + lane < p.n_tri) { A = __ldg(sc.a + c * 32u + lane); B = __ldg(sc.b + c * 32u + lane); C = __ldg(sc.z3 + c * 32u + lane); }
-        advance(pf, pf_pos);
+        advance_live(pf, pf_pos);
     }
     uint32_t stg = 0, phase = 0;
     {
-        for (; c < n_chunks; advance(c, c_pos)) {
+        uint32_t c_after = 0;   // register-prefetch path: the chunk whose data is in flight
+        for (; c < n_chunks; TMA ? advance(c, c_pos) : (void)(c = c_after)) {
             const uint32_t t = c * 32u + lane;
+            ++chunks_done;
             if (TMA) {
                 mbar_wait(&ring.full[stg], phase);
                 A = reinterpret_cast<const float4*>(ring.stage[stg])[lane];
@@ -247,7 +270,8 @@ __global__ void __maxnreg__(72) k_geom3(const __grid_constant__ FrameParams p, c
             if (!TMA) {   // prefetch the next chunk of this warp into registers
                 const uint32_t tn = pf * 32u + lane;
                 if (pf < n_chunks && tn < p.n_tri) { A = __ldg(sc.a + tn); B = __ldg(sc.b + tn); C = __ldg(sc.z3 + tn); }
-                advance(pf, pf_pos);
+                c_after = pf;
+                advance_live(pf, pf_pos);
             }
             // ---- phase A: x'/y' transform, bounds (Triangle::mul, aabb, rasterizer.rs:58-66) --
             const float y1 = xform_row(p.m + 4, v0, v1, v2), x1 = xform_row(p.m + 0, v0, v1, v2);
@@ -457,6 +481,7 @@ __global__ void __maxnreg__(72) k_geom3(const __grid_constant__ FrameParams p, c
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) nfrag_count += __shfl_xor_sync(0xFFFFFFFFu, nfrag_count, d);
         if (lane == 0 && nfrag_count) atomicAdd(&q.aux->frag_counter, (unsigned long long)nfrag_count);
+        if (lane == 0 && chunks_done) atomicAdd(&q.aux->chunks_done, chunks_done);
     }
 }
 
@@ -739,6 +764,50 @@ __global__ void __launch_bounds__(256) k_pack_chunks(const float4* __restrict__ 
 }
 
 // Scene upload: raw soup (9 floats + 3 bytes per triangle) -> the four resident streams.
+// Bounding sphere of every chunk of 32 triangles (object space) for the band cull of k_geom3, and the largest
+// |coordinate| of the scene (bits of a non-negative float in *absmax).  One thread per chunk, once per scene.
+__global__ void __launch_bounds__(128) k_chunk_bounds(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                      const float* __restrict__ z3, uint32_t n_tri, float4* __restrict__ bounds,
+                                                      uint32_t* __restrict__ absmax)
+{
+    const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_chunks = (n_tri + 31u) >> 5;
+    float big = 0.0f;
+    if (chunk < n_chunks) {
+        const uint32_t t0 = chunk * 32u, t1 = min(n_tri, t0 + 32u);
+        float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+        bool finite = true;
+        for (uint32_t t = t0; t < t1; ++t) {
+            const float4 A = a[t], B = b[t];
+            const float v[9] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, z3[t]};
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                lo[k % 3] = fminf(lo[k % 3], v[k]);
+                hi[k % 3] = fmaxf(hi[k % 3], v[k]);
+                finite = finite && fabsf(v[k]) <= 3.0e38f;
+                big = fmaxf(big, fabsf(v[k]));
+            }
+        }
+        const float cx = 0.5f * lo[0] + 0.5f * hi[0], cy = 0.5f * lo[1] + 0.5f * hi[1], cz = 0.5f * lo[2] + 0.5f * hi[2];
+        float r2 = 0.0f;
+        for (uint32_t t = t0; t < t1; ++t) {
+            const float4 A = a[t], B = b[t];
+            const float v[9] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, z3[t]};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float dx = v[3 * k] - cx, dy = v[3 * k + 1] - cy, dz = v[3 * k + 2] - cz;
+                r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
+            }
+        }
+        // rounded up generously: the radius only has to be an upper bound
+        const float r = finite ? sqrtf(r2) * 1.0001f + 1.0e-30f : __int_as_float(0x7FC00000);
+        bounds[chunk] = make_float4(cx, cy, cz, r);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) big = fmaxf(big, __shfl_xor_sync(0xFFFFFFFFu, big, d));
+    if ((threadIdx.x & 31u) == 0u && big > 0.0f) atomicMax(absmax, __float_as_uint(big));
+}
+
 __global__ void __launch_bounds__(256) k_pack_scene(const float* __restrict__ xyz, const uint8_t* __restrict__ rgb,
                                                     uint32_t n, float4* __restrict__ a, float4* __restrict__ b,
                                                     float* __restrict__ z3, uint32_t* __restrict__ col)

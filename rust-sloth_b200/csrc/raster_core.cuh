@@ -38,6 +38,11 @@ struct FrameParams {
     uint32_t count_frags;
     uint32_t debug;    // profiling experiments only (SLOTH_DEBUG): 1 = skip key atomics, 2 = skip row stamps
     char glyph[12];    // 10 glyphs (+pad)
+    // band contexts: whole chunks of 32 triangles are skipped when their bounding sphere (Scene::bounds) cannot
+    // reach the band's rows.  cull_scale = |row 1 of M| (rounded up), cull_pad = bound on the rounding error of
+    // the computed y' of any vertex or sphere centre (both set by the host per frame); 0 = no culling.
+    uint32_t cull_on;
+    float cull_scale, cull_pad;
 };
 
 // Resident scene: 40 B per triangle in four coalesced streams; the geometry kernels read the first
@@ -47,6 +52,7 @@ struct Scene {
     const float4* __restrict__ b;     // v2.y v2.z v3.x v3.y
     const float* __restrict__ z3;     // v3.z
     const uint32_t* __restrict__ rgb; // r | g<<8 | b<<16
+    const float4* __restrict__ bounds; // per chunk of 32 triangles: bounding sphere (centre.xyz, radius), object space
 };
 
 // Transformed triangle + everything hoistable out of the per-candidate loop.

@@ -140,6 +140,30 @@ def test_row_bands_reassemble_to_the_whole_frame():
         assert bad.size == 0, f"bands {W}x{H}/{nb}: {bad.size} cells differ, first {bad[:8]}"
 
 
+def test_row_bands_with_chunk_culling_on_a_large_scene():
+    """Band contexts skip whole chunks of 32 triangles by bounding sphere: many thin bands over a dense mesh
+    (most chunks are culled in every band), rotations that tilt the mesh, even and odd widths, and the cull
+    switched off (SLOTH_DEBUG=4 is read at context creation) must all give the whole frame."""
+    xyz, rgb, s0 = meshes.icosphere(96)                       # 184,320 triangles, 5,760 chunks
+    skull = S.soup("skull")
+    for (scene, W, H, nb, ang) in [((xyz, rgb, s0), 640, 400, 16, (0.3, S.PI + 0.2, 0.1)),
+                                   ((xyz, rgb, s0), 333, 250, 7, (1.1, 0.4, 2.0)),
+                                   (skull, 300, 200, 9, (0.0, S.PI + 0.7, 0.0))]:
+        rot = oracle.rotation(*ang)
+        whole, _, _ = gpu_frame(*scene, W, H, rot)
+        edges = [H * i // nb for i in range(nb + 1)]
+        res = [gpu_frame(*scene, W, H, rot, band=(edges[i], edges[i + 1])) for i in range(nb)]
+        banded = np.concatenate([r[0] for r in res] + [np.full(H, ord(" "), np.uint32)])
+        bad = np.flatnonzero(banded != whole)
+        assert bad.size == 0, f"{W}x{H}/{nb}: {bad.size} cells differ, first {bad[:8]}"
+        n_chunks = (len(scene[0]) + 31) // 32
+        done = [r[2]["chunks_processed"] for r in res]
+        if scene[0] is xyz:   # spatially coherent chunks: the cull must really be in effect
+            assert max(done) < n_chunks and sum(done) < nb * n_chunks // 2, (done, n_chunks)
+    ocells, _, _ = oracle.render(xyz, rgb, s0, 333, 250, oracle.rotation(1.1, 0.4, 2.0), mode=1)
+    assert np.array_equal(gpu_frame(xyz, rgb, s0, 333, 250, oracle.rotation(1.1, 0.4, 2.0))[0], ocells)
+
+
 def test_batch_equals_single_frames_and_is_deterministic():
     xyz, rgb, s0 = S.soup("pikachu")
     pitches = oracle.turntable(0.0, 12)
