@@ -137,6 +137,22 @@ SLOTH_API void *sloth_ctx_stream(sloth_ctx *ctx);
 SLOTH_API int sloth_ctx_set_band(sloth_ctx *ctx, uint32_t row0, uint32_t row1);
 
 /*
+ * Device buffers shared between the processes of one box (one process per GPU), for band mode without a gather
+ * step: the rank that assembles the frame allocates it and exports a handle; every other rank opens the handle
+ * and passes `mapped + 4*row0*W` to sloth_render_device, so its resolve kernel stores the band straight into
+ * the owner's frame over NVLink (peer access is enabled by the open).  sloth_device_read / _write copy between
+ * device memory (own or mapped) and the host on the context's stream and wait.
+ */
+#define SLOTH_IPC_HANDLE_BYTES 64
+SLOTH_API int sloth_device_alloc(int device, size_t bytes, void **d_ptr_out);
+SLOTH_API int sloth_device_free(int device, void *d_ptr);
+SLOTH_API int sloth_ipc_export(int device, const void *d_ptr, unsigned char handle_out[SLOTH_IPC_HANDLE_BYTES]);
+SLOTH_API int sloth_ipc_open(int device, const unsigned char handle[SLOTH_IPC_HANDLE_BYTES], void **d_ptr_out);
+SLOTH_API int sloth_ipc_close(int device, void *d_ptr);
+SLOTH_API int sloth_device_read(sloth_ctx *ctx, const void *d_ptr, void *host_out, size_t bytes);
+SLOTH_API int sloth_device_write(sloth_ctx *ctx, void *d_ptr, const void *host_in, size_t bytes);
+
+/*
  * Context::flush on the device (src/context.rs:50-92).  The exact bytes the
  * reference prints for the cell buffer, produced on the GPU:
  *   mode 0  plain glyphs                                  flush(color = false)   (without println's '\n')

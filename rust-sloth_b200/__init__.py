@@ -51,6 +51,7 @@ ABI_SYMBOLS = [
     "sloth_text_capacity", "sloth_render_text", "sloth_render_text_batch", "sloth_flush_device",
     "sloth_scene_load", "sloth_loader_begin", "sloth_loader_add_obj", "sloth_loader_add_stl", "sloth_loader_commit",
     "sloth_scene_size", "sloth_scene_get",
+    "sloth_device_alloc", "sloth_device_free", "sloth_ipc_export", "sloth_ipc_open", "sloth_ipc_close", "sloth_device_read", "sloth_device_write",
 ]
 
 
@@ -128,8 +129,44 @@ def load_library() -> C.CDLL:
     L.sloth_scene_size.argtypes = [vp]
     L.sloth_scene_size.restype = C.c_size_t
     L.sloth_scene_get.argtypes = [vp, fp, C.POINTER(C.c_uint8), fp]
+    L.sloth_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp)]
+    L.sloth_device_free.argtypes = [C.c_int, vp]
+    L.sloth_ipc_export.argtypes = [C.c_int, vp, C.c_char_p]
+    L.sloth_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.sloth_ipc_close.argtypes = [C.c_int, vp]
+    L.sloth_device_read.argtypes = [vp, vp, vp, C.c_size_t]
+    L.sloth_device_write.argtypes = [vp, vp, vp, C.c_size_t]
     _lib = L
     return L
+
+
+IPC_HANDLE_BYTES = 64
+
+
+def device_alloc(device: int, nbytes: int) -> int:
+    p = C.c_void_p()
+    _check(load_library().sloth_device_alloc(int(device), int(nbytes), C.byref(p)))
+    return int(p.value)
+
+
+def device_free(device: int, ptr: int) -> None:
+    _check(load_library().sloth_device_free(int(device), C.c_void_p(ptr)))
+
+
+def ipc_export(device: int, ptr: int) -> bytes:
+    buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+    _check(load_library().sloth_ipc_export(int(device), C.c_void_p(ptr), buf))
+    return buf.raw
+
+
+def ipc_open(device: int, handle: bytes) -> int:
+    p = C.c_void_p()
+    _check(load_library().sloth_ipc_open(int(device), handle, C.byref(p)))
+    return int(p.value)
+
+
+def ipc_close(device: int, ptr: int) -> None:
+    _check(load_library().sloth_ipc_close(int(device), C.c_void_p(ptr)))
 
 
 def _check(rc: int) -> None:
@@ -349,6 +386,16 @@ class Context:
         n, m = C.c_size_t(0), C.c_float(0.0)
         _check(self._L.sloth_loader_commit(self._h, C.byref(n), C.byref(m)))
         return self._loaded(n, m)
+
+    def read_device(self, ptr: int, n_cells: int) -> np.ndarray:
+        """n_cells uint32 cells from device memory (own or IPC-mapped) to the host."""
+        out = np.empty(int(n_cells), np.uint32)
+        _check(self._L.sloth_device_read(self._h, C.c_void_p(ptr), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def write_device(self, ptr: int, cells: np.ndarray) -> None:
+        cells = np.ascontiguousarray(cells, np.uint32)
+        _check(self._L.sloth_device_write(self._h, C.c_void_p(ptr), cells.ctypes.data_as(C.c_void_p), cells.nbytes))
 
     def scene(self) -> tuple[np.ndarray, np.ndarray, np.float32]:
         """The resident soup read back from the device: (xyz [n,9] f32, rgb [n,3] u8, scene_max)."""

@@ -690,6 +690,69 @@ int sloth_render_device(sloth_ctx* c, const float rot[16], void* d_cells)
 
 void* sloth_ctx_stream(sloth_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
+int sloth_device_alloc(int device, size_t bytes, void** d_ptr_out)
+{
+    if (!d_ptr_out || !bytes) return fail(SLOTH_E_ARG, "d_ptr_out is null or bytes is 0");
+    CU(cudaSetDevice(device));
+    CU(cudaMalloc(d_ptr_out, bytes));   // cudaMalloc, not a pool: only such allocations can be exported
+    return SLOTH_OK;
+}
+
+int sloth_device_free(int device, void* d_ptr)
+{
+    CU(cudaSetDevice(device));
+    CU(cudaFree(d_ptr));
+    return SLOTH_OK;
+}
+
+int sloth_ipc_export(int device, const void* d_ptr, unsigned char handle_out[SLOTH_IPC_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == SLOTH_IPC_HANDLE_BYTES, "handle size");
+    if (!d_ptr || !handle_out) return fail(SLOTH_E_ARG, "d_ptr/handle_out is null");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+    std::memcpy(handle_out, &h, sizeof h);
+    return SLOTH_OK;
+}
+
+int sloth_ipc_open(int device, const unsigned char handle[SLOTH_IPC_HANDLE_BYTES], void** d_ptr_out)
+{
+    if (!handle || !d_ptr_out) return fail(SLOTH_E_ARG, "handle/d_ptr_out is null");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    CU(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return SLOTH_OK;
+}
+
+int sloth_ipc_close(int device, void* d_ptr)
+{
+    CU(cudaSetDevice(device));
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return SLOTH_OK;
+}
+
+int sloth_device_write(sloth_ctx* c, void* d_ptr, const void* host_in, size_t bytes)
+{
+    if (!c) return fail(SLOTH_E_ARG, "null context");
+    if (bytes && (!d_ptr || !host_in)) return fail(SLOTH_E_ARG, "d_ptr/host_in is null");
+    CU(cudaSetDevice(c->device));
+    if (bytes) CU(cudaMemcpyAsync(d_ptr, host_in, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SLOTH_OK;
+}
+
+int sloth_device_read(sloth_ctx* c, const void* d_ptr, void* host_out, size_t bytes)
+{
+    if (!c) return fail(SLOTH_E_ARG, "null context");
+    if (bytes && (!d_ptr || !host_out)) return fail(SLOTH_E_ARG, "d_ptr/host_out is null");
+    CU(cudaSetDevice(c->device));
+    if (bytes) CU(cudaMemcpyAsync(host_out, d_ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SLOTH_OK;
+}
+
 int sloth_ctx_sync(sloth_ctx* c)
 {
     if (!c) return fail(SLOTH_E_ARG, "null context");

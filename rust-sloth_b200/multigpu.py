@@ -1,9 +1,20 @@
-"""One huge frame across the GPUs of a box: destination-row bands + one NCCL all-gather.
+"""One huge frame across the GPUs of a box: destination-row bands, assembled without a gather step.
 
-Every rank keeps the whole scene resident, owns rows [e[r], e[r+1]) (``sloth_ctx_set_band``), runs
-geometry over all triangles but keeps only fragments that land in its band, resolves its band into a
-device buffer, and the bands are exchanged with ``all_gather_into_tensor`` over NVLink (4*W*H/N bytes
-per GPU).  torch is only used for device memory and the collective.
+Every rank keeps the whole scene resident and owns rows [e[r], e[r+1]) (``sloth_ctx_set_band``): its geometry
+kernel skips the chunks of 32 triangles whose bounding sphere cannot reach those rows and keeps only fragments
+that land in the band.  Two ways to put the bands together:
+
+``peer`` (default when the band offsets are 16-byte aligned)
+    The root rank allocates the frame (two of them, used alternately) and exports CUDA IPC handles; every rank
+    maps them and renders its band straight to ``frame + 4*e[r]*W``: the resolve kernel's stores travel over
+    NVLink / NVSwitch while it runs, so there is no collective on the data path at all.  A 4-byte all-reduce per
+    frame (NCCL, on the stream) tells the root that every band has landed and keeps ranks from running more than
+    one frame ahead of the root.
+
+``allgather``
+    Each rank resolves into a local buffer and one ``all_gather_into_tensor`` moves 4*W*H/N bytes per GPU.
+
+torch is only used for the process group, streams and (allgather mode) device memory.
 """
 from __future__ import annotations
 
@@ -13,38 +24,119 @@ from .turntable import band_edges
 
 
 class BandRenderer:
-    def __init__(self, ctx, width: int, height: int, rank: int, world: int, group=None):
+    def __init__(self, ctx, width: int, height: int, rank: int, world: int, group=None, mode: str | None = None,
+                 root: int = 0, depth: int = 1):
         import torch
         import torch.distributed as dist
+        from . import device_alloc, ipc_export, ipc_open
         self.torch, self.dist, self.group = torch, dist, group
-        self.ctx, self.W, self.H, self.rank, self.world = ctx, width, height, rank, world
+        self.ctx, self.W, self.H, self.rank, self.world, self.root = ctx, width, height, rank, world, root
         self.edges = band_edges(height, world)
         self.rows_max = max(self.edges[i + 1] - self.edges[i] for i in range(world))
         ctx.resize(width, height)
         ctx.set_band(self.edges[rank], self.edges[rank + 1])
         dev = torch.device("cuda", ctx.device)
-        # equal-sized slots so that one all_gather_into_tensor moves everything
-        self.local = torch.full((self.rows_max * width,), ord(" "), dtype=torch.int32, device=dev)
-        self.all = torch.empty((world * self.rows_max * width,), dtype=torch.int32, device=dev)
         self.stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
+        aligned = all((e * width) % 4 == 0 for e in self.edges)
+        if mode is None:
+            mode = "peer" if (world > 1 and aligned) else "allgather"
+        if mode == "peer" and not aligned:
+            raise ValueError("peer mode needs band offsets that are multiples of 4 cells (16 bytes)")
+        self.mode = mode
+        self.frame_cells = width * height + height          # image-mode layout: H trailing blank cells
+        self.stride = (self.frame_cells + 3) & ~3           # frame slots stay 16-byte aligned
+        self.depth = max(1, int(depth))                     # frames per render_batch call
+        self.frames, self._owned, self._mapped = [], [], []
+        self.k = 0
+        if mode == "peer":
+            # two regions of `depth` frame slots, used alternately: while the root reads one region the ranks
+            # may already fill the other one
+            n_slots = 2 * self.depth
+            handles = [None]
+            if rank == root:
+                base = device_alloc(ctx.device, 4 * self.stride * n_slots)
+                blank = np.full(self.stride, ord(" "), np.uint32)
+                for i in range(n_slots):
+                    ctx.write_device(base + 4 * self.stride * i, blank)
+                self._owned.append(base)
+                handles[0] = ipc_export(ctx.device, base)
+            if world > 1:
+                dist.broadcast_object_list(handles, src=root, group=group)
+            if rank != root:
+                base = ipc_open(ctx.device, handles[0])
+                self._mapped.append(base)
+            self.frames = [base + 4 * self.stride * i for i in range(n_slots)]
+            self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        else:
+            # equal-sized slots so that one all_gather_into_tensor moves everything
+            self.local = torch.full((self.rows_max * width,), ord(" "), dtype=torch.int32, device=dev)
+            self.all = torch.empty((world * self.rows_max * width,), dtype=torch.int32, device=dev)
+
+    def close(self):
+        from . import device_free, ipc_close
+        self.torch.cuda.synchronize()
+        if self.world > 1 and self.mode == "peer":
+            self.dist.barrier(group=self.group)             # nobody is still writing into the root's frames
+        for p in self._mapped:
+            ipc_close(self.ctx.device, p)
+        self._mapped = []
+        if self.world > 1 and self.mode == "peer":
+            self.dist.barrier(group=self.group)             # all mappings are closed before the owner frees
+        for p in self._owned:
+            device_free(self.ctx.device, p)
+        self._owned = []
 
     def render(self, rot: np.ndarray):
-        """Returns the gathered device tensor (world * rows_max * W int32); rows of band i start at
-        i*rows_max*W."""
+        """Enqueue one frame.  peer mode: returns the device pointer of the assembled frame (meaningful on the
+        root; complete once torch's current stream has passed this call).  allgather mode: returns the gathered
+        device tensor (world * rows_max * W int32; rows of band i start at i*rows_max*W)."""
         torch, dist = self.torch, self.dist
+        cur = torch.cuda.current_stream()
+        if self.mode == "peer":
+            frame = self.frames[(self.k & 1) * self.depth]
+            self.k += 1
+            self.stream.wait_stream(cur)                    # the previous frame's completion signal
+            self.ctx.render_device(rot, frame + 4 * self.edges[self.rank] * self.W)
+            cur.wait_stream(self.stream)
+            if self.world > 1:
+                dist.all_reduce(self.flag, group=self.group)   # every band of this frame has landed
+            return frame
         self.ctx.render_device(rot, self.local.data_ptr())
-        ev = torch.cuda.Event()
-        ev.record(self.stream)
-        torch.cuda.current_stream().wait_event(ev)
+        cur.wait_stream(self.stream)
         if self.world > 1:
             dist.all_gather_into_tensor(self.all, self.local, group=self.group)
         else:
             self.all.copy_(self.local)
         return self.all
 
-    def to_frame(self, gathered, image: bool = True) -> np.ndarray:
-        """Host cell buffer in the reference's layout (W*H cells, +H blank cells in image mode)."""
-        g = gathered.cpu().numpy().view(np.uint32)
+    def render_batch(self, rots: np.ndarray):
+        """peer mode only: up to `depth` frames in one call.  Inside it the geometry of frame k+1 overlaps the
+        resolve of frame k, i.e. the NVLink stores of one frame are hidden behind the next frame's geometry, and
+        there is one completion signal for the whole batch.  Returns the frame pointers (root)."""
+        if self.mode != "peer":
+            raise ValueError("render_batch needs peer mode")
+        rots = np.ascontiguousarray(rots, np.float32).reshape(-1, 16)
+        n = rots.shape[0]
+        if n > self.depth:
+            raise ValueError(f"{n} frames in one batch, but the renderer was created with depth={self.depth}")
+        torch, dist = self.torch, self.dist
+        cur = torch.cuda.current_stream()
+        first = (self.k & 1) * self.depth
+        self.k += 1
+        self.stream.wait_stream(cur)
+        self.ctx.render_device_batch(rots, self.frames[first] + 4 * self.edges[self.rank] * self.W, self.stride)
+        cur.wait_stream(self.stream)
+        if self.world > 1:
+            dist.all_reduce(self.flag, group=self.group)
+        return self.frames[first:first + n]
+
+    def to_frame(self, result, image: bool = True) -> np.ndarray:
+        """Host cell buffer in the reference's layout (W*H cells, +H blank cells in image mode); call it on the
+        root in peer mode."""
+        if self.mode == "peer":
+            self.torch.cuda.current_stream().synchronize()
+            return self.ctx.read_device(result, self.frame_cells if image else self.W * self.H)
+        g = result.cpu().numpy().view(np.uint32)
         parts = [g[i * self.rows_max * self.W:i * self.rows_max * self.W + (self.edges[i + 1] - self.edges[i]) * self.W]
                  for i in range(self.world)]
         cells = np.concatenate(parts)

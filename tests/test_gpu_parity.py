@@ -235,10 +235,34 @@ def test_band_renderer_single_process():
     rot = oracle.rotation(0.0, S.PI, 0.0)
     ctx = rs.Context.blank(True)
     ctx.set_scene(xyz, rgb, s0)
-    br = multigpu.BandRenderer(ctx, 320, 200, 0, 1)
-    frame = br.to_frame(br.render(rot))
     ocells, _, _ = oracle.render(xyz, rgb, s0, 320, 200, rot, mode=0)
-    assert np.array_equal(frame, ocells)
+    for mode in ("allgather", "peer"):
+        # "peer": the frame lives in an exported cudaMalloc buffer and the band is resolved into it at its row
+        # offset (with more ranks the same pointer arithmetic runs on an IPC mapping, profiles/band_8k.py)
+        br = multigpu.BandRenderer(ctx, 320, 200, 0, 1, mode=mode, depth=3)
+        assert br.mode == mode
+        for _ in range(3):                                   # both frame regions get used
+            frame = br.to_frame(br.render(rot))
+            assert np.array_equal(frame, ocells), mode
+        if mode == "peer":
+            rot2 = oracle.rotation(0.1, S.PI + 0.5, 0.0)
+            o2, _, _ = oracle.render(xyz, rgb, s0, 320, 200, rot2, mode=0)
+            for _ in range(2):
+                ptrs = br.render_batch(np.stack([rot, rot2, rot]))
+                assert [np.array_equal(br.to_frame(p), o) for p, o in zip(ptrs, (ocells, o2, ocells))] == [True] * 3
+        br.close()
+    ctx.close()
+
+
+def test_ipc_helpers_round_trip():
+    """sloth_device_alloc / write / read / ipc_export on one process (opening needs a second process)."""
+    ctx = rs.Context.blank(True)
+    p = rs.device_alloc(ctx.device, 4 * 1000)
+    cells = np.arange(1000, dtype=np.uint32)
+    ctx.write_device(p, cells)
+    assert np.array_equal(ctx.read_device(p + 4 * 10, 990), cells[10:])
+    assert len(rs.ipc_export(ctx.device, p)) == rs.IPC_HANDLE_BYTES
+    rs.device_free(ctx.device, p)
     ctx.close()
 
 
