@@ -35,7 +35,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsloth_b200.so")
+LIB_PATH = os.environ.get("SLOTH_B200_LIB") or os.path.join(_HERE, "libsloth_b200.so")   # override: A/B builds while profiling
 HOST_LIB_PATH = os.path.join(_HERE, "libsloth_host.so")
 
 SLOTH_OK, SLOTH_E_ARG, SLOTH_E_CUDA, SLOTH_E_STATE, SLOTH_E_TOO_LARGE = 0, -1, -2, -3, -4
