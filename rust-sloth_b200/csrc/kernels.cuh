@@ -85,8 +85,8 @@ struct TmaRing {
 // ---------------------------------------------------------------------------------
 // k_geom3: the geometry kernel, warp-autonomous (no block barriers).
 //
-// Persistent warps walk the triangle stream in batches of 16 consecutive chunks of
-// 32 triangles (lane = triangle):
+// Persistent warps walk the triangle stream in chunks of 32 triangles (lane = triangle),
+// chunk i on warp i mod n_warps (or in short runs of consecutive chunks, see capi.cu):
 //   A  prefetched 16+16+8 B loads, x'/y' transform (z' is not needed unless a
 //      fragment is found), bounds, row stamps, classification.
 //   cull  a triangle whose computed orientation is negative by more than the
@@ -108,7 +108,7 @@ static constexpr uint32_t G3_WARPS = 8;          // warps per block
 #ifndef G3_BLOCKS_PER_SM
 #define G3_BLOCKS_PER_SM 3
 #endif
-static constexpr uint32_t G3_BATCH_MAX = 16;     // consecutive chunks per warp turn (fewer for small scenes)
+static constexpr uint32_t G3_BATCH_MAX = 16;     // upper limit of the consecutive-chunks-per-turn knob (default 1, see capi.cu)
 static constexpr uint32_t G3_RING = 64;          // per-warp ring of covering triangles (power of two)
 
 struct G3Queue {
