@@ -80,3 +80,14 @@ def test_flush_formats():
                                                       b'<span style="color:rgb(0,0,0)"> ')
     ansi = rs.flush_bytes(cells[:1], True, False, False)
     assert ansi == b"\x1b[1;1H\x1b[48;2;25;25;25m\x1b[38;2;1;2;3m@\x1b[0m"
+
+
+def test_integration_md_shows_a_binding_for_every_entry_point():
+    """INTEGRATION.md is the reference-side binding a maintainer would add: nothing the header declares is missing."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "sloth_b200.h")).read()
+    integ = open(os.path.join(root, "INTEGRATION.md")).read()
+    syms = set(re.findall(r"SLOTH_API\s+[\w\s\*]+?\b(sloth_\w+)\s*\(", hdr))
+    assert len(syms) >= 40
+    assert sorted(s for s in syms if s not in integ) == []
