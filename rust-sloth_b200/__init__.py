@@ -230,8 +230,22 @@ def _host_lib() -> C.CDLL:
         H.sloth_host_load.argtypes = [C.c_char_p]
         H.sloth_host_load.restype = C.POINTER(_HostScene)
         H.sloth_host_free.argtypes = [C.POINTER(_HostScene)]
+        H.sloth_host_parse_f32.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.c_size_t]
+        H.sloth_host_parse_f32.restype = C.c_size_t
         _host = H
     return _host
+
+
+def parse_f32_tokens(tokens) -> tuple[np.ndarray, np.ndarray]:
+    """The device loader's decimal -> f32 routine (csrc/dec_float.cuh) compiled for the host: (values, status)
+    with status 0 = ok, 1 = not a number, 2 = not decided (see loader.cuh).  For the CPU tests."""
+    text = "\n".join(tokens).encode()
+    out = np.zeros(len(tokens), np.float32)
+    status = np.zeros(len(tokens), np.uint8)
+    n = _host_lib().sloth_host_parse_f32(text, len(text), out.ctypes.data_as(C.POINTER(C.c_float)),
+                                         status.ctypes.data_as(C.POINTER(C.c_uint8)), len(tokens))
+    assert n == len(tokens), "empty tokens are not allowed"
+    return out, status
 
 
 def match_meshes(arg: str) -> list[SimpleMesh]:

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "mesh_io.hpp"
+#include "../csrc/dec_float.cuh"   // the device loader's decimal -> f32 routine, compiled for the host
 
 extern "C" {
 
@@ -59,5 +60,27 @@ __attribute__((visibility("default"))) void sloth_host_free(sloth_host_scene* s)
     std::free(s->mesh_sizes);
     std::free(s->mesh_bbox);
     std::free(s);
+}
+
+// The decimal -> f32 conversion of the device loader (csrc/dec_float.cuh), run on the host so that the CPU test
+// suite can compare it with strtof on millions of tokens.  Tokens are separated by '\n'; status[i] is 0 (ok),
+// 1 (not a number) or 2 (outside what the routine decides); out[i] is written for status 0.
+__attribute__((visibility("default"))) size_t sloth_host_parse_f32(const char* text, size_t len, float* out, uint8_t* status,
+                                                                   size_t cap)
+{
+    size_t n = 0, b = 0;
+    for (size_t i = 0; i <= len && n < cap; ++i) {
+        if (i == len || text[i] == '\n') {
+            if (i > b) {
+                float f = 0.0f;
+                status[n] = (uint8_t)sloth::ld::parse_float(reinterpret_cast<const unsigned char*>(text + b),
+                                                            reinterpret_cast<const unsigned char*>(text + i), f);
+                out[n] = f;
+                ++n;
+            }
+            b = i + 1;
+        }
+    }
+    return n;
 }
 }

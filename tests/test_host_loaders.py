@@ -99,3 +99,80 @@ def test_bundled_models_match_the_committed_soups():
         assert rs.scene_scale0(meshes) == s0
     two = rs.match_meshes(MODELS + "suzy.obj " + MODELS + "suzy.obj")
     assert sum(len(m) for m in two) == 1936
+
+
+# ---- the device loader's decimal -> f32 conversion, run on the host (csrc/dec_float.cuh) ------------------------
+def _strtof(tokens):
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.strtof.restype = ctypes.c_float
+    libc.strtof.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+    return np.array([libc.strtof(t.encode(), None) for t in tokens], np.float32)
+
+
+def _fuzz_tokens(rng, n):
+    toks = []
+    f32 = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    for i in range(n):
+        kind, v = i % 8, float(f32[i])
+        if kind == 0 and np.isfinite(v) and 1e-15 < abs(v) < 1e15:
+            toks.append("%.9g" % v)                                  # shortest round trip of a random f32
+        elif kind == 1:
+            toks.append("%.6f" % rng.uniform(-1000, 1000))           # what Blender writes
+        elif kind == 2:
+            toks.append("%.17g" % rng.uniform(-10, 10))              # repr of a double
+        elif kind == 3:                                              # random digit strings, up to 19 digits
+            nd = int(rng.integers(1, 20))
+            digits = "".join(str(d) for d in rng.integers(0, 10, nd))
+            frac = int(rng.integers(0, nd + 1))
+            ex = int(rng.integers(-27 + frac, 9 + frac))             # decimal exponent stays inside [-27, 27]
+            body = digits[:nd - frac] + ("." + digits[nd - frac:] if frac or rng.integers(2) else "")
+            if body.startswith("."):
+                body = ("0" if rng.integers(2) else "") + body
+            toks.append(("-" if rng.integers(2) else "+" if rng.integers(4) == 0 else "") + body +
+                        (("e%d" if rng.integers(2) else "E%+d") % ex if ex or rng.integers(2) else ""))
+        elif kind == 4:                                              # integers around 2^24 .. 2^26: exact ties
+            toks.append(str(int(rng.integers(2**24 - 64, 2**26))))
+        elif kind == 5:                                              # halfway points with short expansions
+            k = int(rng.integers(1, 2**23))
+            toks.append("%d.%s" % (k, "5" if rng.integers(2) else "50000000001" if rng.integers(2) else "49999999999"))
+        elif kind == 6 and np.isfinite(v) and 1e-20 < abs(v) < 1e20:  # exact midpoint of two neighbouring f32, in full
+            import fractions
+            a = np.float32(abs(v)); b = np.nextafter(a, np.float32(np.inf))
+            mid = (fractions.Fraction(float(a)) + fractions.Fraction(float(b))) / 2
+            num, den = mid.numerator, mid.denominator                # den is a power of two
+            k = den.bit_length() - 1
+            toks.append("%d.%s" % (num >> k, str((num & (den - 1)) * 5**k).rjust(k, "0")) if k else str(num))
+        else:
+            toks.append("%.8e" % rng.uniform(-1e6, 1e6))
+    return toks
+
+
+def test_device_decimal_to_f32_routine_matches_strtof_on_the_host():
+    rng = np.random.default_rng(11)
+    toks = _fuzz_tokens(rng, 200000)
+    got, status = rs.parse_f32_tokens(toks)
+    want = _strtof(toks)
+    decided = status == 0
+    assert not (status == 1).any(), [t for t, s in zip(toks, status) if s == 1][:5]
+    bad = np.flatnonzero(decided & (got.view(np.uint32) != want.view(np.uint32)))
+    assert bad.size == 0, [(toks[i], got[i], want[i]) for i in bad[:8]]
+    # only the long exact-midpoint expansions may be left undecided, and most tokens are decided
+    undecided = [t for t, s in zip(toks, status) if s == 2]
+    assert all(len(t.replace(".", "").replace("-", "").lstrip("0")) > 19 for t in undecided), undecided[:5]
+    assert decided.mean() > 0.9
+
+
+def test_device_decimal_routine_grammar():
+    toks = ["1", "-0", "+.5", "5.", "1e5", "1E-5", "007", "0.000", "-0.0e9", "1e", ".", "-", "+", "1.2.3", "1f", "0x10",
+            "abc", "nan", "inf", "-Infinity", "1e40", "1e-40", "340282356779733661637539395458142568448",
+            "340282346638528859811704183484516925440", "0.00000000000000000000000000000000000001"]
+    got, status = rs.parse_f32_tokens(toks)
+    want = _strtof(toks)
+    # the 39-digit number at index 22 is FLT_MAX + half an ulp exactly (the overflow boundary): left undecided
+    expect = [0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 0, 2]
+    assert list(status) == expect, list(zip(toks, status))
+    for t, g, w, s in zip(toks, got, want, status):
+        if s == 0:
+            assert np.float32(g).view(np.uint32) == np.float32(w).view(np.uint32), (t, g, w)
+    assert np.signbit(got[1]) and np.signbit(got[8]) and got[23] == np.float32(3.4028235e38)
