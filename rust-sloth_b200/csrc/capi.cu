@@ -206,6 +206,12 @@ void build_params(const sloth_ctx* c, const float rot[16], FrameParams& p)
     p.row0 = band ? c->row0 : 0;
     p.row1 = band ? c->row1 : c->H;
     p.krow0 = p.row0 - (c->halo_slots ? 1u : 0u);
+    p.srow0 = p.row0;
+    p.srow1 = p.row1;
+    if (c->W == 1u) {   // one column: the stamp of row y is cell y+1, i.e. (row y+1, column 0)
+        p.srow0 = p.row0 ? p.row0 - 1u : 0u;
+        p.srow1 = p.row1 - 1u;
+    }
     p.n_tri = c->n_tri;
     p.image = c->image ? 1u : 0u;
     p.count_frags = (c->stat_flags & 1u) ? 1u : 0u;

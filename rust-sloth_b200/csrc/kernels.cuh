@@ -301,7 +301,7 @@ __global__ void __maxnreg__(72) k_geom3(const __grid_constant__ FrameParams p, c
             // neighbours on screen, so their rows fall into a 64-row window: two REDUX.OR give
             // the chunk's row set, then lane i owns rows i and 32+i of the window (conflict-free).
             // Branch-free: with nothing to stamp the need words are 0 and no atomic is issued.
-            const uint32_t sy0 = BAND ? max(miny, p.row0) : miny, sy1 = BAND ? min(maxy, p.row1) : maxy;
+            const uint32_t sy0 = BAND ? max(miny, p.srow0) : miny, sy1 = BAND ? min(maxy, p.srow1) : maxy;
             const bool st = do_stamps && has_rows && sy0 < sy1;
             bool tall = false;   // rows outside the 64-row window: stamped in the rare block below
             if (do_stamps) {
@@ -708,8 +708,15 @@ __global__ void __launch_bounds__(256) k_resolve_odd(const __grid_constant__ Fra
         else if (ka != KEY_EMPTY) kw = ka;
         else if (kb != KEY_EMPTY) kw = kb;
         if (kw != KEY_EMPTY) c = cell_of(p, sc, kw);
+        // the stamp of row y is cell y*W + 1 (rasterizer.rs:90): column 1 of row y, or -- in a frame that is one
+        // column wide -- column 0 of row y+1
         row = id / p.W;
-        stamped = p.image && id % p.W == 1u && q.rowmax[row] != 0u;
+        bool stamp_cell = id % p.W == 1u;
+        if (p.W == 1u) {
+            stamp_cell = id >= 1u;
+            row = id - (stamp_cell ? 1u : 0u);
+        }
+        stamped = p.image && stamp_cell && q.rowmax[row] != 0u;
     }
     if (p.image) {
         const bool contested = stamped && kw != KEY_EMPTY;

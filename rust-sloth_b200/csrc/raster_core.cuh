@@ -33,6 +33,8 @@ struct FrameParams {
     uint32_t XS;       // key step per pixel x: 1 (W even) or 2 (W odd)
     uint32_t row0, row1;  // destination-row band owned by this context ([0,H) = whole frame)
     uint32_t krow0;    // first row of the key plane: row0, or row0-1 (halo) for odd W bands
+    uint32_t srow0, srow1;  // rows whose newline stamp (cell y*W+1) lands in this context's cells: [row0,row1) --
+                       // except for W == 1, where that cell is (row y+1, column 0): [row0-1, row1-1)
     uint32_t n_tri;
     uint32_t image;    // Context.image
     uint32_t count_frags;

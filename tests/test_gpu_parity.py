@@ -286,6 +286,34 @@ def test_newline_stamp_vs_wrapped_fragment_order():
     assert hits > 0   # the exact same-chunk check was exercised
 
 
+def test_one_column_frames_keep_their_newline_stamps():
+    """W == 1: no x candidate exists, but the newline stamp of row y is cell y*W+1 = (row y+1, column 0)
+    (found by the hypothesis fuzz: nine degenerate triangles and one that spans a row, 1x4)."""
+    tris = np.zeros((10, 9), np.float32)
+    tris[9, 7] = -1.0
+    rgb = np.full((10, 3), 7, np.uint8)
+    rot = oracle.rotation(0.0, 0.0, 0.0)
+    ocells, oz, _ = oracle.render(tris, rgb, 1.0, 1, 4, rot, image=True, mode=0)
+    assert ocells[3] == ord("\n")
+    cells, z, _ = gpu_frame(tris, rgb, np.float32(1.0), 1, 4, rot)
+    assert_same(cells, z, ocells, oz, "1x4")
+    for seed in range(12):
+        xyz, rgb, s0 = meshes.random_soup(seed, 30)
+        for H in (2, 5, 9, 40):
+            rot = oracle.rotation(0.1 * seed, S.PI + 0.3 * seed, 0.0)
+            for image in (True, False):
+                ocells, oz, _ = oracle.render(xyz, rgb, s0, 1, H, rot, image=image, mode=0)
+                cells, z, _ = gpu_frame(xyz, rgb, s0, 1, H, rot, image=image)
+                assert_same(cells, z, ocells, oz, f"1x{H} seed {seed}")
+            # the same frame in row bands: a stamp lands in the band below the row that was stamped
+            ocells, _, _ = oracle.render(xyz, rgb, s0, 1, H, rot, image=True, mode=0)
+            nb = min(3, H)
+            edges = [H * i // nb for i in range(nb + 1)]
+            parts = [gpu_frame(xyz, rgb, s0, 1, H, rot, band=(edges[i], edges[i + 1]))[0] for i in range(nb)]
+            banded = np.concatenate(parts + [np.full(H, ord(" "), np.uint32)])
+            assert np.array_equal(banded, ocells), f"1x{H} seed {seed} in {nb} bands"
+
+
 def test_tall_frame_uses_global_row_stamps():
     xyz, rgb, s0 = S.soup("suzy")
     rot = oracle.rotation(0.0, S.PI, 0.0)
@@ -421,7 +449,7 @@ _coord = st.one_of(
     st.sampled_from([0.0, -0.0, 1.0, -1.0, 0.5, 0.25, 1e-30, -1e-30, 1e-45, 3e38, -3e38, float("inf"), float("-inf"), float("nan")]))
 
 
-@settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=int(os.environ.get("HYP_EXAMPLES", "120")), deadline=None, suppress_health_check=list(HealthCheck))
 @given(tris=st.lists(st.lists(_coord, min_size=9, max_size=9), min_size=1, max_size=40),
        W=st.integers(min_value=1, max_value=70), H=st.integers(min_value=1, max_value=40),
        angles=st.tuples(st.floats(-7, 7, width=32), st.floats(-7, 7, width=32), st.floats(-7, 7, width=32)),
