@@ -224,3 +224,29 @@ def test_fuzz_three_statements_agree(tris, W, H, angles, image, s0):
     assert k0["covered"] == k1["covered"] and k0["zwrites"] == k1["zwrites"]
     c2, z2 = restate_np.render(xyz, rgb, s0, W, H, rot, image=image)
     assert np.array_equal(c0, c2) and np.array_equal(z0.view(np.uint32), z2.view(np.uint32))
+
+
+def test_narrow_frames_agree_between_the_two_restatements():
+    """W = 1, 2, 3: no or hardly any x candidates, but newline stamps still land at cell y*W+1 -- for W = 1 that is
+    column 0 of the NEXT row (rasterizer.rs:89-91 indexes the flat buffer).  Both restatements must agree there;
+    this is the behaviour the GPU path was fixed to follow (tests/test_gpu_parity.py::test_one_column_frames_*)."""
+    from rust_sloth_b200 import meshes
+    tris = np.zeros((10, 9), np.float32)
+    tris[9, 7] = -1.0                                     # the hypothesis counter-example: one triangle spanning row 2
+    rgb = np.full((10, 3), 7, np.uint8)
+    cells, _, _ = oracle.render(tris, rgb, 1.0, 1, 4, oracle.rotation(0.0, 0.0, 0.0), image=True, mode=0)
+    assert list(cells) == [32, 32, 32, 10, 32, 32, 32, 32]
+    stamped = 0
+    for seed in range(8):
+        xyz, rgb, s0 = meshes.random_soup(seed, 30)
+        rot = oracle.rotation(0.1 * seed, 3.1 + 0.3 * seed, 0.0)
+        for W in (1, 2, 3):
+            for H in (2, 5, 9, 40):
+                for image in (True, False):
+                    cells, z, _ = oracle.render(xyz, rgb, s0, W, H, rot, image=image, mode=0)
+                    c2, z2 = restate_np.render(xyz, rgb, s0, W, H, rot, image=image)
+                    assert np.array_equal(cells, c2) and np.array_equal(z.view(np.uint32), z2.view(np.uint32)), (seed, W, H)
+                    m1, _, _ = oracle.render(xyz, rgb, s0, W, H, rot, image=image, mode=1)
+                    assert np.array_equal(cells, m1)
+                    stamped += int((cells == 10).sum())
+    assert stamped > 50
