@@ -579,6 +579,7 @@ int sloth_ctx_destroy(sloth_ctx* c)
     cudaFree(c->sc_z3);
     cudaFree(c->sc_rgb);
     cudaFree(c->sc_chunks);
+    cudaFree(c->sc_bounds);
     for (int i = 0; i < 2; ++i) { cudaFree(c->walk_tri[i]); cudaFree(c->walk_base[i]); cudaFree(c->irr_tri[i]); }
     for (int i = 0; i < EV_N; ++i) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) {
