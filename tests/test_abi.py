@@ -87,3 +87,45 @@ def test_integration_md_shows_a_binding_for_every_entry_point():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     integ = open(os.path.join(root, "INTEGRATION.md")).read()
     assert sorted(s for s in rs.ABI_SYMBOLS if s not in integ) == []   # ABI_SYMBOLS == the header, see above
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """include/sloth_b200.h must be consumable by a C compiler (the boundary is a C ABI, no C++ or torch types), and
+    a C caller must link: it calls the host-side helpers and checks that context creation fails cleanly without a GPU
+    (or succeeds with one)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "sloth_b200.h"
+int main(void) {
+    float rot[16], ut[16], pitches[8];
+    sloth_rotation_from_euler(0.0f, 3.14159274f, 0.0f, rot);
+    sloth_utransform(80, 40, 7.5f, ut);
+    size_t n = sloth_turntable_pitches(0.0f, 4, pitches, 8);
+    sloth_ctx *ctx = NULL;
+    int rc = sloth_ctx_create(0, 1, &ctx);
+    if (rc == SLOTH_OK) { rc = sloth_ctx_destroy(ctx); if (rc != SLOTH_OK) return 3; }
+    else if (rc != SLOTH_E_CUDA || strlen(sloth_last_error()) == 0) return 2;
+    printf("%zu %.1f %.1f\n", n, (double)ut[12], (double)ut[13]);
+    return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    lib_dir = os.path.dirname(rs.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L", lib_dir, "-lsloth_b200", f"-Wl,-rpath,{lib_dir}"], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["4", "20.0", "20.0"]      # W/4 and H/2 of Context::update's matrix (context.rs:115-132)
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="a GPU is present")
+def test_cli_fails_loudly_without_a_gpu(tmp_path):
+    """The drop-in `sloth` binary has no CPU path either: without a device it must exit non-zero with the CUDA error."""
+    exe = os.path.join(os.path.dirname(rs.LIB_PATH), "bin", "sloth")
+    obj = tmp_path / "t.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    r = subprocess.run([exe, str(obj), "image", "-w", "20", "-h", "10"], capture_output=True, text=True)
+    assert r.returncode != 0 and r.stdout == ""
+    assert "cuda" in r.stderr.lower()
