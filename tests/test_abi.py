@@ -129,3 +129,22 @@ def test_cli_fails_loudly_without_a_gpu(tmp_path):
     r = subprocess.run([exe, str(obj), "image", "-w", "20", "-h", "10"], capture_output=True, text=True)
     assert r.returncode != 0 and r.stdout == ""
     assert "cuda" in r.stderr.lower()
+
+
+def test_cli_surface_follows_the_reference_clap_definition():
+    """src/inputs.rs:9-85: required arguments, help/version, unknown flags -- all decided before
+    any GPU work, so this runs anywhere."""
+    exe = os.path.join(os.path.dirname(rs.LIB_PATH), "bin", "sloth")
+    run = lambda *a: subprocess.run([exe, *a], capture_output=True, text=True)
+    r = run()
+    assert r.returncode == 1 and "required arguments were not provided" in r.stderr and "<input filename(s)>" in r.stderr
+    r = run("model.obj", "image")
+    assert r.returncode == 1 and "-w <width>" in r.stderr
+    r = run("model.obj", "image", "-w")
+    assert r.returncode == 1 and "requires a value" in r.stderr
+    r = run("model.obj", "--frobnicate")
+    assert r.returncode == 1 and "wasn't expected" in r.stderr
+    r = run("--help")
+    assert r.returncode == 0 and r.stdout.startswith("Sloth 0.1") and "image -w <width> [-h <height>] [-j, --webify <frame count>]" in r.stdout
+    r = run("-V")
+    assert r.returncode == 0 and r.stdout.strip() == "Sloth 0.1"
