@@ -250,3 +250,60 @@ def test_narrow_frames_agree_between_the_two_restatements():
                     assert np.array_equal(cells, m1)
                     stamped += int((cells == 10).sum())
     assert stamped > 50
+
+
+def test_back_face_proof_never_discards_a_covering_triangle():
+    """DESIGN.md section 3, `backface_proven` (csrc/kernels.cuh): a triangle whose computed orientation satisfies
+    A_c < -2^-18 * L * D is dropped by the GPU path without looking at any candidate.  Brute force over the
+    reference's whole scan domain in strict float32 (numpy restates rasterizer.rs:30-36,58-75): whenever the criterion
+    fires, no candidate may pass the three edge tests.  The sample leans on the dangerous cases: slivers and
+    nearly collinear triangles of either orientation, tiny and huge coordinates."""
+    F = np.float32
+    rng = np.random.default_rng(5)
+    fired = covered_total = fired_tiny_margin = 0
+    for it in range(6000):
+        W, H = [(64, 48), (33, 57), (200, 16)][it % 3]
+        scale = F([1.0, 1.0, 30.0, 1e3, 1e-2][it % 5])
+        a = rng.uniform(-20, 80, 2)
+        b = a + rng.uniform(-40, 40, 2)
+        t = rng.uniform(-0.5, 1.5)
+        off = rng.normal() * 10.0 ** rng.uniform(-7, 1)                 # distance of the third vertex from the line a-b
+        if it % 4 == 0:
+            off = rng.uniform(-30, 30)                                  # ordinary triangles as well
+        d = b - a
+        nrm = np.array([-d[1], d[0]]) / (np.hypot(*d) + 1e-12)
+        c = a + t * d + off * nrm
+        v = (np.stack([a, b, c]) * scale).astype(F)
+        if it % 2:
+            v = v[[0, 2, 1]]
+        (x1, y1), (x2, y2), (x3, y3) = v
+        wm1, hm1 = F(W - 1), F(H - 1)
+        with np.errstate(all="ignore"):
+            mn0, mx0 = min(x1, x2, x3), max(x1, x2, x3)
+            mn1, mx1 = min(y1, y2, y3), max(y1, y2, y3)
+            # the criterion, operation by operation as in backface_proven
+            dx1, dy1, dx2, dy2 = F(x1 - x3), F(y1 - y3), F(x2 - x1), F(y2 - y1)
+            area = F(F(dy2 * dx1) - F(dx2 * dy1))
+            L = max(F(mx0 - mn0), F(mx1 - mn1))
+            D = max(F(max(abs(mn0), abs(mx0)) + wm1), F(max(abs(mn1), abs(mx1)) + hm1))
+            T = F(F(L * D) * F(3.814697265625e-06))
+            proven = bool(T > F(1e-30) and area < -T)
+            # the reference's scan domain and coverage test
+            minx = int(np.ceil(max(mn0, F(1.0)))); miny = int(np.ceil(max(mn1, F(1.0))))
+            maxx = int(np.ceil(min(F(mx0 * F(2.0)), wm1))); maxy = int(np.ceil(min(mx1, hm1)))
+            covered = 0
+            if maxx > minx and maxy > miny:
+                px = np.arange(minx, maxx, dtype=np.int64).astype(F)[None, :]
+                py = np.arange(miny, maxy, dtype=np.int64).astype(F)[:, None]
+
+                def orient(ax, ay, bx, by):
+                    return (F(bx - ax) * (py - ay).astype(F)).astype(F) - (F(by - ay) * (px - ax).astype(F)).astype(F)
+                w0, w1, w2 = orient(x2, y2, x3, y3), orient(x3, y3, x1, y1), orient(x1, y1, x2, y2)
+                covered = int(((w0.astype(F) >= 0) & (w1.astype(F) >= 0) & (w2.astype(F) >= 0)).sum())
+        covered_total += covered > 0
+        if proven:
+            fired += 1
+            fired_tiny_margin += bool(area > F(-4.0) * T)
+            assert covered == 0, (v.tolist(), float(area), float(T), covered)
+    # the sample must exercise both outcomes, including criterion hits close to the threshold
+    assert fired > 1000 and covered_total > 100 and fired_tiny_margin > 20, (fired, covered_total, fired_tiny_margin)
