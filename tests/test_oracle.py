@@ -307,3 +307,62 @@ def test_back_face_proof_never_discards_a_covering_triangle():
             assert covered == 0, (v.tolist(), float(area), float(T), covered)
     # the sample must exercise both outcomes, including criterion hits close to the threshold
     assert fired > 1000 and covered_total > 100 and fired_tiny_margin > 20, (fired, covered_total, fired_tiny_margin)
+
+
+def test_band_chunk_cull_bound_is_conservative():
+    """Row bands skip a chunk of 32 triangles when its bounding sphere cannot reach the band (k_geom3 `culled`,
+    k_chunk_bounds, build_params in csrc/).  Restated in strict float32 / float64 exactly as the kernels and the host
+    compute it, and checked against the per-triangle band condition of phase A on random chunks whose bands are placed
+    right at the edge of the chunk's row range: a culled chunk must not contain a triangle the band would keep."""
+    F = np.float32
+    rng = np.random.default_rng(9)
+    culled_n = kept_n = near_miss = 0
+    for it in range(3000):
+        W, H = [(640, 400), (333, 250), (7680, 4320), (80, 40)][it % 4]
+        size = 10.0 ** rng.uniform(-3, 4)
+        centre = rng.uniform(-1, 1, 3) * size
+        spread = size * 10.0 ** rng.uniform(-3, 0)
+        tri = (centre + rng.uniform(-1, 1, (32, 3, 3)) * spread).astype(F)
+        absmax = F(max(np.abs(tri).max(), size))                      # the scene is at least as large as the chunk
+        s0 = F(size)
+        rot = oracle.rotation(*rng.uniform(-3.2, 3.2, 3))
+        M = oracle.mat4_mul(oracle.utransform(W, H, s0), rot).reshape(4, 4).T   # (row, col)
+        m4, m5, m6, m7 = (F(M[1, k]) for k in range(4))
+
+        def yprime(p):   # xform_row: ((m0*x + m1*y) + m2*z) + m3, every operation rounded
+            return F(F(F(F(m4 * p[..., 0]) + F(m5 * p[..., 1])) + F(m6 * p[..., 2])) + m7)
+        with np.errstate(all="ignore"):
+            y = yprime(tri).astype(F)                                   # (32, 3)
+            mn1, mx1 = y.min(axis=1), y.max(axis=1)
+            miny = np.ceil(np.maximum(mn1, F(1.0))).astype(np.int64)
+            maxy = np.ceil(np.minimum(mx1, F(H - 1))).astype(np.int64)
+            # k_chunk_bounds
+            lo, hi = tri.reshape(-1, 3).min(axis=0), tri.reshape(-1, 3).max(axis=0)
+            c = (F(0.5) * lo + F(0.5) * hi).astype(F)
+            dlt = (tri.reshape(-1, 3) - c).astype(F)
+            r2 = F(((dlt[:, 0] * dlt[:, 0]).astype(F) + (dlt[:, 1] * dlt[:, 1]).astype(F)).astype(F) + (dlt[:, 2] * dlt[:, 2]).astype(F)).max()
+            r = F(F(np.sqrt(F(r2))) * F(1.0001) + F(1e-30))
+            # build_params (double on the host)
+            norm = float(np.sqrt(float(m4) ** 2 + float(m5) ** 2 + float(m6) ** 2)) * 1.0001
+            mag = (abs(float(m4)) + abs(float(m5)) + abs(float(m6))) * float(absmax) + abs(float(m7))
+            pad = mag * 2.0 ** -19 + 1.0e-3
+            if not (np.isfinite(norm) and np.isfinite(pad) and pad < 1.0e6):
+                continue
+            cull_scale, cull_pad = F(norm), F(pad * 1.0001)
+            yc = yprime(c)
+            R = F(F(r * cull_scale) + cull_pad)
+            # bands right at the edge of the chunk's rows, above and below, with and without the odd-width halo row
+            top, bot = int(miny.min()), int(maxy.max())
+            for row0, row1 in [(bot + k, bot + k + 7) for k in (-1, 0, 1, 2, 3)] + [(max(0, top - k - 7), max(1, top - k)) for k in (-1, 0, 1, 2, 3)]:
+                if row1 <= row0:
+                    continue
+                for krow0 in {row0, max(0, row0 - 1)}:
+                    culled = bool(F(yc - R) >= F(row1) or F(F(yc + R) + F(2.0)) <= F(krow0))
+                    keeps = (miny < maxy) & (miny < row1) & (maxy + 1 > krow0)     # has_rows of the BAND variants
+                    if culled:
+                        culled_n += 1
+                        assert not keeps.any(), (it, row0, row1, krow0, float(yc), float(R), miny[keeps][:4], maxy[keeps][:4])
+                    else:
+                        kept_n += 1
+                        near_miss += not keeps.any()
+    assert culled_n > 3000 and kept_n > 3000, (culled_n, kept_n)
