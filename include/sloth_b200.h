@@ -68,6 +68,22 @@ SLOTH_API int sloth_scene_set(sloth_ctx *ctx, const float *xyz, const uint8_t *r
                               float scene_max);
 
 /*
+ * The same mesh queue before to_simple_mesh de-indexes it (geometry.rs:99-107 reads
+ * positions[indices[..]]; tobj's Mesh and stl_io's IndexedMesh are both indexed):
+ *   positions  n_vert*3 floats, indices  n_tri*3 vertex ids in draw order (meshes concatenated, ids offset by
+ *   the caller), rgb / scene_max as above.  SLOTH_E_ARG when an id is >= n_vert.
+ * Both entry points end in the same resident scene: corners are deduplicated by exact bit pattern, and when
+ * triangles share vertices the frame path runs Triangle::mul (geometry.rs:43-48) once per unique vertex
+ * (k_xform) instead of once per triangle corner -- bit-identical, since the product is a pure function of the
+ * vertex.  sloth_ctx_set_path (before the scene is set) pins the choice: AUTO picks the indexed path at <= 1.5
+ * unique vertices per triangle, SOUP / INDEXED force one (tests, profiling).
+ */
+SLOTH_API int sloth_scene_set_indexed(sloth_ctx *ctx, const float *positions, size_t n_vert, const uint32_t *indices,
+                                      const uint8_t *rgb, size_t n_tri, float scene_max);
+enum { SLOTH_PATH_AUTO = 0, SLOTH_PATH_SOUP = 1, SLOTH_PATH_INDEXED = 2 };
+SLOTH_API int sloth_ctx_set_path(sloth_ctx *ctx, int path);
+
+/*
  * Model loading on the device: match_meshes (inputs.rs:95-129: tobj 3.2.2 / stl_io 0.4.2) and
  * to_meshes (geometry.rs:83-189: de-indexed soup, fan triangulation, colour rules, bounding boxes) for files of
  * any size.  The file's bytes go to the GPU once; line splitting, decimal -> f32 conversion (correctly rounded,
@@ -192,6 +208,9 @@ typedef struct sloth_stats {
     uint32_t chunks_processed; /* last frame: chunks of 32 triangles the geometry kernel did not band-cull; needs count_fragments */
     float load_read_ms, load_parse_ms, load_commit_ms; /* last sloth_scene_load: file -> pinned memory, copy + device
                                                           parse, soup -> resident scene (host wall clock) */
+    uint32_t n_vert;           /* unique vertices of the resident scene (0 when it renders through the soup path) */
+    uint32_t geom_path;        /* SLOTH_PATH_SOUP or SLOTH_PATH_INDEXED: what the resident scene uses */
+    float xform_ms;            /* per-vertex transform kernel of the last sloth_render when timing is on (indexed path) */
 } sloth_stats;
 
 SLOTH_API int sloth_stats_get(sloth_ctx *ctx, sloth_stats *out);

@@ -40,10 +40,12 @@ HOST_LIB_PATH = os.path.join(_HERE, "libsloth_host.so")
 
 SLOTH_OK, SLOTH_E_ARG, SLOTH_E_CUDA, SLOTH_E_STATE, SLOTH_E_TOO_LARGE = 0, -1, -2, -3, -4
 SLOTH_E_IO, SLOTH_E_PARSE, SLOTH_E_UNSUPPORTED = -5, -6, -7
+PATH_AUTO, PATH_SOUP, PATH_INDEXED = 0, 1, 2   # sloth_ctx_set_path
 
 # every symbol include/sloth_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "sloth_ctx_create", "sloth_ctx_destroy", "sloth_scene_set", "sloth_ctx_resize", "sloth_render",
+    "sloth_ctx_create", "sloth_ctx_destroy", "sloth_scene_set", "sloth_scene_set_indexed", "sloth_ctx_set_path",
+    "sloth_ctx_resize", "sloth_render",
     "sloth_render_batch", "sloth_render_device", "sloth_ctx_sync", "sloth_ctx_set_band",
     "sloth_shader_set", "sloth_stats_get", "sloth_stats_enable", "sloth_last_error",
     "sloth_rotation_from_euler", "sloth_utransform", "sloth_turntable_pitches", "sloth_cells_per_frame",
@@ -70,6 +72,7 @@ class Stats(C.Structure):
         ("resolve_ms", C.c_float),
         ("chunks_processed", C.c_uint32),
         ("load_read_ms", C.c_float), ("load_parse_ms", C.c_float), ("load_commit_ms", C.c_float),
+        ("n_vert", C.c_uint32), ("geom_path", C.c_uint32), ("xform_ms", C.c_float),
     ]
 
     def as_dict(self) -> dict:
@@ -93,6 +96,8 @@ def load_library() -> C.CDLL:
     L.sloth_ctx_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
     L.sloth_ctx_destroy.argtypes = [vp]
     L.sloth_scene_set.argtypes = [vp, fp, C.POINTER(C.c_uint8), C.c_size_t, C.c_float]
+    L.sloth_scene_set_indexed.argtypes = [vp, fp, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.c_size_t, C.c_float]
+    L.sloth_ctx_set_path.argtypes = [vp, C.c_int]
     L.sloth_ctx_resize.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.sloth_render.argtypes = [vp, fp, C.POINTER(C.c_uint32), fp]
     L.sloth_render_batch.argtypes = [vp, fp, C.c_size_t, C.POINTER(C.c_uint32)]
@@ -333,10 +338,12 @@ class PinnedBuffer:
 class Context:
     """context.rs:12-19.  Owns one GPU context; not thread-safe (one per thread / GPU)."""
 
-    def __init__(self, image: bool, device: int = 0):
+    def __init__(self, image: bool, device: int = 0, path: int | None = None):
         self._L = load_library()
         self._h = C.c_void_p()
         _check(self._L.sloth_ctx_create(device, 1 if image else 0, C.byref(self._h)))
+        if path is not None:
+            _check(self._L.sloth_ctx_set_path(self._h, int(path)))
         self.image = bool(image)
         self.device = device
         self.width = 0
@@ -351,8 +358,12 @@ class Context:
         self._z = None
 
     @classmethod
-    def blank(cls, image: bool, device: int = 0) -> "Context":
-        return cls(image, device)
+    def blank(cls, image: bool, device: int = 0, path: int | None = None) -> "Context":
+        return cls(image, device, path)
+
+    def set_path(self, path: int) -> None:
+        """PATH_AUTO / PATH_SOUP / PATH_INDEXED for the scenes set from now on (sloth_ctx_set_path)."""
+        _check(self._L.sloth_ctx_set_path(self._h, int(path)))
 
     def close(self):
         if self._h:
@@ -373,6 +384,18 @@ class Context:
                                        xyz.shape[0], np.float32(scene_max)))
         self._scene_max = np.float32(scene_max)
         self.n_tri = xyz.shape[0]
+
+    def set_scene_indexed(self, positions: np.ndarray, indices: np.ndarray, rgb: np.ndarray, scene_max: float) -> None:
+        """The mesh queue before de-indexing (geometry.rs:99-107): positions (v,3) f32, indices (n,3) u32, rgb (n,3) u8."""
+        positions = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        indices = np.ascontiguousarray(indices, np.uint32).reshape(-1, 3)
+        rgb = np.ascontiguousarray(rgb, np.uint8).reshape(-1, 3)
+        assert rgb.shape[0] == indices.shape[0]
+        _check(self._L.sloth_scene_set_indexed(self._h, _fp(positions), positions.shape[0],
+                                               indices.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                               rgb.ctypes.data_as(C.POINTER(C.c_uint8)), indices.shape[0], np.float32(scene_max)))
+        self._scene_max = np.float32(scene_max)
+        self.n_tri = indices.shape[0]
 
     # -- device loaders (inputs.rs:95-129 + geometry.rs:83-189 on the GPU) ----------------
     def _loaded(self, n: C.c_size_t, m: C.c_float) -> tuple[int, np.float32]:

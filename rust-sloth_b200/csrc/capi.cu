@@ -15,10 +15,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <new>
 
 #include "../../include/sloth_b200.h"
 #include "kernels.cuh"
+#include "index.cuh"
+#include "tri_kernel.cuh"
 #include "flush.cuh"
 #include "loader.cuh"
 
@@ -64,7 +67,7 @@ void mat4_mul(const float* A, const float* B, float* C)
 const float k_default_thr[9] = {0.20f, 0.30f, 0.40f, 0.50f, 0.60f, 0.70f, 0.80f, 0.90f, 1.0f};
 const char k_default_glyph[10] = {'.', ':', '-', '=', '+', '*', '#', '%', '@', ' '};
 
-enum { EV_START = 0, EV_GEOM, EV_WALK, EV_RESOLVE_BEGIN, EV_END, EV_N };
+enum { EV_START = 0, EV_XFORM, EV_GEOM, EV_WALK, EV_RESOLVE_BEGIN, EV_END, EV_N };
 
 }  // namespace
 
@@ -91,6 +94,17 @@ struct sloth_ctx {
     uint32_t n_tri = 0;
     float scene_max = 0.0f;
     bool have_scene = false;
+
+    // indexed scene (index.cuh): unique vertices + per-triangle records, transformed once per frame by k_xform
+    int path_pref = SLOTH_PATH_AUTO;  // sloth_ctx_set_path / SLOTH_PATH
+    bool indexed = false;             // the resident scene renders through k_xform + k_tri
+    uint32_t n_vert = 0;
+    float* sc_pos = nullptr;          // x[n_vert+1] y[n_vert+1] z[n_vert+1] (one allocation, SoA)
+    size_t pos_stride = 0;            // floats between the x, y and z arrays
+    uint4* sc_rec = nullptr;          // [n_tri padded to 32]
+    float2* vxy = nullptr;            // [n_vert + 1], rewritten every frame
+    float* vz = nullptr;
+    uint32_t tri_blocks_per_sm = T_BLOCKS_PER_SM;   // SLOTH_TGRID overrides (profiling)
 
     // frame state
     uint32_t W = 0, H = 0;
@@ -219,6 +233,18 @@ void build_params(const sloth_ctx* c, const float rot[16], FrameParams& p)
     // band cull (k_geom3): |row 1 of M| rounded up, and a bound on the rounding error of any computed y' -- four
     // roundings of terms that are at most (|m4|+|m5|+|m6|) * absmax + |m7| in magnitude, counted twice (vertex and
     // sphere centre) with a factor 4 to spare.  Only for scenes whose coordinates are all finite and <= 2^20.
+    // k_tri's frame-wide distance bound for the back-face proof: |x'| <= (|m0|+|m1|+|m2|) * absmax + |m3| for every
+    // vertex (same for y'), so D_frame = max(Xabs + (W-1), Yabs + (H-1)) >= every triangle's D; 0.1 % covers the
+    // roundings of the computed coordinates and of the bound.  Unknown extent -> +inf (nothing is ever proven).
+    p.bf_k = std::numeric_limits<float>::infinity();
+    if (c->scene_clean) {
+        const double am = (double)c->scene_absmax;
+        const double xa = (std::fabs((double)p.m[0]) + std::fabs((double)p.m[1]) + std::fabs((double)p.m[2])) * am + std::fabs((double)p.m[3]);
+        const double ya = (std::fabs((double)p.m[4]) + std::fabs((double)p.m[5]) + std::fabs((double)p.m[6])) * am + std::fabs((double)p.m[7]);
+        const double D = std::max(xa + (double)p.wm1, ya + (double)p.hm1) * 1.001;
+        const float k = (float)(D * 3.814697265625e-06 * 1.0001);   // 2^-18 D, rounded up
+        if (std::isfinite(k)) p.bf_k = std::nextafterf(k, std::numeric_limits<float>::infinity());
+    }
     p.cull_on = 0u;
     p.cull_scale = p.cull_pad = 0.0f;
     if (band && c->scene_clean && !(c->debug & 4u)) {
@@ -245,12 +271,79 @@ Queues make_queues(const sloth_ctx* c, int set)
     return q;
 }
 
+Scene scene_of(const sloth_ctx* c)
+{
+    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb, c->sc_bounds, c->sc_rec, c->vxy, c->vz};
+    return sc;
+}
+
+// Kernels that run side by side on one SM (the geometry kernel of frame k+1 with k_tail / k_resolve of frame k)
+// must agree on the L1 / shared-memory split, or the SM has to drain before it can switch: one carveout for all
+// frame kernels, re-applied only when it changes.
+int apply_carveout(sloth_ctx* c, int pct)
+{
+    if (c->carveout_override >= 0) pct = c->carveout_override;
+    if (pct == c->carveout_set) return SLOTH_OK;
+    const cudaFuncAttribute a = cudaFuncAttributePreferredSharedMemoryCarveout;
+    CU(cudaFuncSetAttribute(k_tail, a, pct));
+    CU(cudaFuncSetAttribute(k_resolve_even, a, pct));
+    CU(cudaFuncSetAttribute(k_resolve_odd, a, pct));
+    CU(cudaFuncSetAttribute(k_clear_keys_odd, a, pct));
+    CU(cudaFuncSetAttribute(k_xform, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<false, false>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<false, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<true, false>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<true, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_geom3<false, false, false>, a, pct));
+    CU(cudaFuncSetAttribute(k_geom3<false, true, false>, a, pct));
+    CU(cudaFuncSetAttribute(k_geom3<true, false, false>, a, pct));
+    CU(cudaFuncSetAttribute(k_geom3<true, true, false>, a, pct));
+    CU(cudaFuncSetAttribute(k_geom3<false, false, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_geom3<false, true, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_geom3<true, false, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_geom3<true, true, true>, a, pct));
+    c->carveout_set = pct;
+    return SLOTH_OK;
+}
+
+// Indexed path: k_xform (Triangle::mul once per unique vertex) then k_tri, both on stream `st`.
+int enqueue_geometry_indexed(sloth_ctx* c, const FrameParams& p, const Scene& sc, const Queues& q, int set, cudaStream_t st,
+                             bool kt)
+{
+    const uint32_t n_chunks = (c->n_tri + 31) / 32;
+    const uint32_t bps = c->tri_blocks_per_sm;
+    const uint32_t grid = std::min<uint32_t>((n_chunks + T_WARPS - 1) / T_WARPS, (uint32_t)c->sm_count * bps);
+    // a clean scene under a bounded matrix cannot produce |x'|,|y'| > 2^40: skip the per-triangle test
+    bool bounded = c->scene_clean;
+    for (int i = 0; i < 8; ++i) bounded = bounded && std::fabs(p.m[i]) <= 131072.0f;
+    const uint32_t rowmax_shared = c->rowmax_bytes <= 33024u ? 1u : 0u;
+    const size_t dyn = rowmax_shared ? c->rowmax_bytes : 0;
+    const bool band_mode = c->row1 != 0;
+    void (*kern)(FrameParams, Scene, unsigned long long*, Queues, uint32_t) =
+        bounded ? (band_mode ? k_tri<false, true> : k_tri<false, false>) : (band_mode ? k_tri<true, true> : k_tri<true, false>);
+    {
+        const size_t per_block = sizeof(TRing) * T_WARPS + dyn + 1024;
+        int pct = (int)((per_block * bps * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
+        pct = std::min(100, std::max(25, pct));
+        const int rc = apply_carveout(c, pct);
+        if (rc) return rc;
+    }
+    const float* px = c->sc_pos;
+    k_xform<<<(c->n_vert + 1 + 255) / 256, 256, 0, st>>>(p, px, px + c->pos_stride, px + 2 * c->pos_stride, c->n_vert, c->vxy, c->vz);
+    if (kt) CU(cudaEventRecord(c->ev[EV_XFORM], st));
+    kern<<<grid, T_WARPS * 32, dyn, st>>>(p, sc, c->keys[set], q, rowmax_shared);
+    c->launches += 2;
+    if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
+    return SLOTH_OK;
+}
+
 // Geometry pass of a frame (aux clear, k_geom3) on stream `st`, into frame-state set `set`.
 int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st, bool kt)
 {
-    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb, c->sc_bounds};
+    const Scene sc = scene_of(c);
     const Queues q = make_queues(c, set);
     CU(cudaMemsetAsync(c->aux_region[set], 0, c->aux_bytes, st));
+    if (c->indexed && c->n_tri) return enqueue_geometry_indexed(c, p, sc, q, set, st, kt);
     if (c->n_tri) {
         {
             const uint32_t n_chunks = (c->n_tri + 31) / 32;
@@ -277,23 +370,13 @@ int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t s
                                     : (band_mode ? k_geom3<true, true, true> : k_geom3<true, false, true>);
             else kern = bounded ? (band_mode ? k_geom3<false, true, false> : k_geom3<false, false, false>)
                                 : (band_mode ? k_geom3<true, true, false> : k_geom3<true, false, false>);
-            if (dyn > 16384) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
             {
-                // Kernels that run side by side on one SM (k_geom3 of frame k+1 with k_tail / k_resolve of frame k)
-                // must agree on the L1 / shared-memory split, or the SM has to drain before it can switch.  Ask
-                // for one carveout that holds three geometry blocks and apply it to all frame kernels.
+                // one carveout that holds three geometry blocks, shared by all frame kernels (apply_carveout)
                 const size_t per_block = sizeof(G3Queue) * G3_WARPS + dyn + 1024;
                 int pct = (int)((per_block * blocks_per_sm * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
                 pct = std::min(100, std::max(50, pct));
-                if (c->carveout_override >= 0) pct = c->carveout_override;
-                if (pct != c->carveout_set) {
-                    CU(cudaFuncSetAttribute(k_tail, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-                    CU(cudaFuncSetAttribute(k_resolve_even, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-                    CU(cudaFuncSetAttribute(k_resolve_odd, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-                    CU(cudaFuncSetAttribute(k_clear_keys_odd, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-                    c->carveout_set = pct;
-                }
-                CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                const int rc = apply_carveout(c, pct);
+                if (rc) return rc;
             }
             kern<<<grid, G3_WARPS * 32, dyn, st>>>(p, sc, c->sc_chunks, c->keys[set], q, batch_chunks, rowmax_shared);
         }
@@ -307,7 +390,7 @@ int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t s
 int enqueue_tail(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
 {
     if (!c->n_tri) return SLOTH_OK;
-    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb, c->sc_bounds};
+    const Scene sc = scene_of(c);
     const Queues q = make_queues(c, set);
     const uint32_t wb = (uint32_t)c->sm_count * c->tail_blocks_per_sm, ib = std::max<uint32_t>(1u, (uint32_t)c->sm_count / 2u);
     k_tail<<<wb + ib, 128, 0, st>>>(p, sc, c->keys[set], q, wb);
@@ -318,7 +401,7 @@ int enqueue_tail(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
 // Resolve half of a frame (optional z plane, key plane -> cells, key plane reset) on stream `st`.
 int enqueue_resolve(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st, uint32_t* d_out, float* d_z)
 {
-    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb, c->sc_bounds};
+    const Scene sc = scene_of(c);
     const Queues q = make_queues(c, set);
     const bool band = c->row1 != 0;
     const uint32_t rows = p.row1 - p.row0;
@@ -453,11 +536,92 @@ int check_ready(sloth_ctx* c)
     return SLOTH_OK;
 }
 
+void free_index(sloth_ctx* c)
+{
+    cudaFree(c->sc_pos); cudaFree(c->sc_rec); cudaFree(c->vxy); cudaFree(c->vz);
+    c->sc_pos = nullptr; c->sc_rec = nullptr; c->vxy = nullptr; c->vz = nullptr;
+    c->indexed = false;
+    c->n_vert = 0;
+    c->pos_stride = 0;
+}
+
+// Room for n_vert unique vertices (+ the sentinel) and the records of n_tri triangles (padded to 32).
+int alloc_index(sloth_ctx* c, size_t n_vert, size_t n_tri)
+{
+    c->pos_stride = (n_vert + 1 + 63) & ~(size_t)63;
+    const size_t n_padded = (n_tri + 31) & ~(size_t)31;
+    CU(cudaMalloc(&c->sc_pos, 3 * c->pos_stride * sizeof(float)));
+    CU(cudaMalloc(&c->sc_rec, std::max<size_t>(n_padded, 32) * sizeof(uint4)));
+    CU(cudaMalloc(&c->vxy, (n_vert + 1) * sizeof(float2)));
+    CU(cudaMalloc(&c->vz, (n_vert + 1) * sizeof(float)));
+    c->n_vert = (uint32_t)n_vert;
+    return SLOTH_OK;
+}
+
+// Deduplicate the corners of the resident soup by bit pattern (index.cuh) and decide whether the scene renders
+// through the indexed path: SLOTH_PATH_AUTO takes it when triangles share vertices (at most 1.5 unique vertices
+// per triangle; a soup without sharing has 3 and is better off with k_geom3).
+int build_index(sloth_ctx* c, size_t n_tri)
+{
+    free_index(c);
+    if (!n_tri || c->path_pref == SLOTH_PATH_SOUP) return SLOTH_OK;
+    const Scene sc = scene_of(c);
+    const size_t n_corners = 3 * n_tri;
+    size_t cap = 64;
+    while (cap < 2 * n_corners) cap <<= 1;
+    const uint32_t n_blocks = (uint32_t)((n_corners + ix::SCAN_BLOCK - 1) / ix::SCAN_BLOCK);
+    uint32_t *table = nullptr, *rep = nullptr, *block_sum = nullptr;
+    auto drop = [&]() { cudaFree(table); cudaFree(rep); cudaFree(block_sum); };
+#define CU_IX(call)                                                                                \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            drop();                                                                                \
+            free_index(c);                                                                         \
+            return fail(SLOTH_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                          \
+    } while (0)
+    CU_IX(cudaMalloc(&table, cap * sizeof(uint32_t)));
+    CU_IX(cudaMalloc(&rep, n_corners * sizeof(uint32_t)));
+    CU_IX(cudaMalloc(&block_sum, (n_blocks + 1) * sizeof(uint32_t)));
+    CU_IX(cudaMemsetAsync(table, 0xFF, cap * sizeof(uint32_t), c->stream));
+    const unsigned cb = (unsigned)((n_corners + 255) / 256);
+    ix::k_ix_insert<<<cb, 256, 0, c->stream>>>(sc, (uint32_t)n_corners, table, (uint32_t)(cap - 1));
+    ix::k_ix_lookup<<<cb, 256, 0, c->stream>>>(sc, (uint32_t)n_corners, table, (uint32_t)(cap - 1), rep);
+    ix::k_ix_flag_sums<<<n_blocks, 256, 0, c->stream>>>(rep, (uint32_t)n_corners, block_sum);
+    ix::k_ix_scan_sums<<<1, 1024, 0, c->stream>>>(block_sum, n_blocks, block_sum + n_blocks);
+    c->launches += 4;
+    uint32_t n_vert = 0;
+    CU_IX(cudaMemcpyAsync(&n_vert, block_sum + n_blocks, sizeof n_vert, cudaMemcpyDeviceToHost, c->stream));
+    CU_IX(cudaStreamSynchronize(c->stream));
+    CU_IX(cudaGetLastError());
+    const bool take = c->path_pref == SLOTH_PATH_INDEXED || (size_t)n_vert * 2 <= n_tri * 3;
+    if (take) {
+        const int rc = alloc_index(c, n_vert, n_tri);
+        if (rc) { drop(); free_index(c); return rc; }
+        uint32_t* rank = table;   // the table is not needed any more: its memory holds the ranks
+        float* px = c->sc_pos;
+        ix::k_ix_rank<<<n_blocks, 256, 0, c->stream>>>(sc, rep, (uint32_t)n_corners, block_sum, rank, px, px + c->pos_stride,
+                                                      px + 2 * c->pos_stride);
+        const size_t n_padded = (n_tri + 31) & ~(size_t)31;
+        ix::k_ix_records<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(rep, rank, (uint32_t)n_tri, (uint32_t)n_padded, n_vert,
+                                                                                  c->sc_rec);
+        c->launches += 2;
+        CU_IX(cudaGetLastError());
+        CU_IX(cudaStreamSynchronize(c->stream));
+        c->indexed = true;
+    }
+#undef CU_IX
+    drop();
+    return SLOTH_OK;
+}
+
 // Drop the resident scene and allocate room for n_tri triangles (plus the per-scene queues).
 int alloc_scene(sloth_ctx* c, size_t n_tri)
 {
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->resolve_stream));
+    free_index(c);
     cudaFree(c->sc_a); cudaFree(c->sc_b); cudaFree(c->sc_z3); cudaFree(c->sc_rgb); cudaFree(c->sc_chunks); cudaFree(c->sc_bounds);
     c->sc_chunks = nullptr;
     c->sc_bounds = nullptr;
@@ -503,7 +667,7 @@ int finish_scene(sloth_ctx* c, size_t n_tri)
     }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
-    return SLOTH_OK;
+    return build_index(c, n_tri);
 }
 
 }  // namespace
@@ -540,6 +704,8 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     if (const char* g = std::getenv("SLOTH_TAIL")) c->tail_blocks_per_sm = (uint32_t)std::max(1, std::atoi(g));
     if (const char* g = std::getenv("SLOTH_BATCH")) c->batch_max = (uint32_t)std::min(16, std::max(1, std::atoi(g)));
     if (const char* g = std::getenv("SLOTH_GRID")) c->geom_blocks_per_sm = (uint32_t)std::max(1, std::atoi(g));
+    if (const char* g = std::getenv("SLOTH_TGRID")) c->tri_blocks_per_sm = (uint32_t)std::min((int)T_BLOCKS_PER_SM, std::max(1, std::atoi(g)));
+    if (const char* g = std::getenv("SLOTH_PATH")) c->path_pref = std::min(2, std::max(0, std::atoi(g)));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     {
@@ -558,6 +724,18 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
         // (profiles/README.md, "overlap variance").
         CU(cudaEventCreateWithFlags(&c->ev_geom_done[i], cudaEventDefault));
         CU(cudaEventCreateWithFlags(&c->ev_resolved[i], cudaEventDisableTiming));
+    }
+    {   // dynamic shared memory of the soup kernel (TMA rings + per-block row stamps) can exceed the default limit
+        const cudaFuncAttribute a = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        const int lim = 64 * 1024;
+        CU(cudaFuncSetAttribute(k_geom3<false, false, false>, a, lim));
+        CU(cudaFuncSetAttribute(k_geom3<false, true, false>, a, lim));
+        CU(cudaFuncSetAttribute(k_geom3<true, false, false>, a, lim));
+        CU(cudaFuncSetAttribute(k_geom3<true, true, false>, a, lim));
+        CU(cudaFuncSetAttribute(k_geom3<false, false, true>, a, lim));
+        CU(cudaFuncSetAttribute(k_geom3<false, true, true>, a, lim));
+        CU(cudaFuncSetAttribute(k_geom3<true, false, true>, a, lim));
+        CU(cudaFuncSetAttribute(k_geom3<true, true, true>, a, lim));
     }
     *out = c;
     return SLOTH_OK;
@@ -580,6 +758,7 @@ int sloth_ctx_destroy(sloth_ctx* c)
     cudaFree(c->sc_rgb);
     cudaFree(c->sc_chunks);
     cudaFree(c->sc_bounds);
+    free_index(c);
     for (int i = 0; i < 2; ++i) { cudaFree(c->walk_tri[i]); cudaFree(c->walk_base[i]); cudaFree(c->irr_tri[i]); }
     for (int i = 0; i < EV_N; ++i) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) {
@@ -629,6 +808,64 @@ int sloth_scene_set(sloth_ctx* c, const float* xyz, const uint8_t* rgb, size_t n
     c->n_tri = (uint32_t)n_tri;
     c->scene_max = scene_max;
     c->have_scene = true;
+    return SLOTH_OK;
+}
+
+int sloth_scene_set_indexed(sloth_ctx* c, const float* positions, size_t n_vert, const uint32_t* indices, const uint8_t* rgb,
+                            size_t n_tri, float scene_max)
+{
+    if (!c) return fail(SLOTH_E_ARG, "null context");
+    if (n_tri && (!positions || !indices || !rgb || !n_vert)) return fail(SLOTH_E_ARG, "positions/indices/rgb is null or n_vert is 0");
+    if (n_tri > MAX_TRIS) return fail(SLOTH_E_TOO_LARGE, "%zu triangles; the depth key holds a 27-bit index (max %u)", n_tri, MAX_TRIS);
+    if (n_vert >= 0xFFFFFFFFull) return fail(SLOTH_E_TOO_LARGE, "%zu vertices; vertex ids are 32-bit", n_vert);
+    CU(cudaSetDevice(c->device));
+    int rc = alloc_scene(c, n_tri);
+    if (rc) return rc;
+    if (n_tri) {
+        float* d_pos = nullptr;
+        uint32_t* d_idx = nullptr;
+        uint8_t* d_rgb = nullptr;
+        uint32_t* d_bad = nullptr;
+        auto drop = [&]() { cudaFree(d_pos); cudaFree(d_idx); cudaFree(d_rgb); cudaFree(d_bad); };
+        cudaError_t e = cudaMalloc(&d_pos, n_vert * 3 * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&d_idx, n_tri * 3 * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&d_rgb, n_tri * 3);
+        if (e == cudaSuccess) e = cudaMalloc(&d_bad, sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_pos, positions, n_vert * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, indices, n_tri * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_rgb, rgb, n_tri * 3, cudaMemcpyHostToDevice, c->stream);
+        uint32_t bad = 0;
+        if (e == cudaSuccess) {
+            ix::k_ix_expand_input<<<(unsigned)((n_tri + 255) / 256), 256, 0, c->stream>>>(d_pos, (uint32_t)n_vert, d_idx, d_rgb, (uint32_t)n_tri,
+                                                                                        c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb, d_bad);
+            c->launches += 1;
+            e = cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        drop();
+        if (e != cudaSuccess) return fail(SLOTH_E_CUDA, "sloth_scene_set_indexed: %s", cudaGetErrorString(e));
+        if (bad) return fail(SLOTH_E_ARG, "%u triangles reference a vertex id >= n_vert (%zu)", bad, n_vert);
+        rc = finish_scene(c, n_tri);
+        if (rc) return rc;
+    }
+    {   // finite and |v| <= 2^20 everywhere?  Unreferenced vertices only make the answer conservative.
+        bool clean = true;
+        for (size_t i = 0; i < n_vert * 3 && clean; ++i) clean = std::fabs(positions[i]) <= 1048576.0f;
+        c->scene_clean = clean || n_tri == 0;
+    }
+    c->n_tri = (uint32_t)n_tri;
+    c->scene_max = scene_max;
+    c->have_scene = true;
+    return SLOTH_OK;
+}
+
+int sloth_ctx_set_path(sloth_ctx* c, int path)
+{
+    if (!c) return fail(SLOTH_E_ARG, "null context");
+    if (path != SLOTH_PATH_AUTO && path != SLOTH_PATH_SOUP && path != SLOTH_PATH_INDEXED)
+        return fail(SLOTH_E_ARG, "path must be SLOTH_PATH_AUTO, _SOUP or _INDEXED");
+    c->path_pref = path;   // takes effect at the next sloth_scene_set / _set_indexed / loader commit
     return SLOTH_OK;
 }
 
@@ -954,6 +1191,8 @@ int sloth_stats_get(sloth_ctx* c, sloth_stats* out)
     out->load_read_ms = c->load_ms[0];
     out->load_parse_ms = c->load_ms[1];
     out->load_commit_ms = c->load_ms[2];
+    out->n_vert = c->indexed ? c->n_vert : 0u;
+    out->geom_path = c->indexed ? (uint32_t)SLOTH_PATH_INDEXED : (uint32_t)SLOTH_PATH_SOUP;
     if (c->sized && c->aux_region[c->last_set]) {
         FrameAux aux;
         CU(cudaMemcpy(&aux, c->aux_region[c->last_set] + c->rowmax_bytes, sizeof aux, cudaMemcpyDeviceToHost));
@@ -974,7 +1213,12 @@ int sloth_stats_get(sloth_ctx* c, sloth_stats* out)
         if (c->last_was_batch) out->last_frame_ms = c->batch_ms_per_frame;
         else CU(cudaEventElapsedTime(&out->last_frame_ms, c->ev[EV_START], c->ev[EV_END]));
         if (c->ev_kernels_valid && !c->last_was_batch) {
-            CU(cudaEventElapsedTime(&out->geom_ms, c->ev[EV_START], c->ev[EV_GEOM]));
+            if (c->indexed && c->n_tri) {
+                CU(cudaEventElapsedTime(&out->xform_ms, c->ev[EV_START], c->ev[EV_XFORM]));
+                CU(cudaEventElapsedTime(&out->geom_ms, c->ev[EV_XFORM], c->ev[EV_GEOM]));
+            } else {
+                CU(cudaEventElapsedTime(&out->geom_ms, c->ev[EV_START], c->ev[EV_GEOM]));
+            }
             CU(cudaEventElapsedTime(&out->walk_ms, c->ev[EV_GEOM], c->ev[EV_WALK]));
             CU(cudaEventElapsedTime(&out->resolve_ms, c->ev[EV_RESOLVE_BEGIN], c->ev[EV_END]));
         }

@@ -45,6 +45,9 @@ struct FrameParams {
     // the computed y' of any vertex or sphere centre (both set by the host per frame); 0 = no culling.
     uint32_t cull_on;
     float cull_scale, cull_pad;
+    // indexed path (k_tri), bounded scenes only: 2^-18 * D_frame, D_frame >= the distance bound D of every
+    // triangle's back-face proof (backface_proven), rounded up on the host
+    float bf_k;
 };
 
 // Resident scene: 40 B per triangle in four coalesced streams; the geometry kernels read the first
@@ -55,6 +58,10 @@ struct Scene {
     const float* __restrict__ z3;     // v3.z
     const uint32_t* __restrict__ rgb; // r | g<<8 | b<<16
     const float4* __restrict__ bounds; // per chunk of 32 triangles: bounding sphere (centre.xyz, radius), object space
+    // indexed path (index.cuh): per-triangle vertex ids, and the per-frame output of k_xform
+    const uint4* __restrict__ rec;     // (i0, i1, i2, 0) per triangle, padded to a multiple of 32 with the sentinel vertex
+    const float2* __restrict__ vxy;    // (x', y') per unique vertex
+    const float* __restrict__ vz;      // z' per unique vertex
 };
 
 // Transformed triangle + everything hoistable out of the per-candidate loop.

@@ -1,0 +1,332 @@
+// tri_kernel.cuh -- k_tri: the geometry kernel of the indexed path (sm_100a).
+//
+// Same job as k_geom3 (draw_triangle's prologue and candidate loop, rasterizer.rs:56-91, for every triangle of the
+// scene), restructured around the per-vertex stage: k_xform has already applied Triangle::mul to every unique
+// vertex, so a triangle costs one 16-byte record load plus three 8-byte gathers of (x', y') from an L2-resident
+// array instead of nine coordinate loads and 36 un-fusable multiplies/adds.
+//
+// Persistent warps, lane = triangle, chunk i -> warp i mod n_warps, two-deep software pipeline (record of chunk
+// k+2 and gathers of chunk k+1 in flight while chunk k is computed):
+//   A  bounds (aabb, rasterizer.rs:58-66), image-mode row stamps (32-row window per chunk, one REDUX.MIN +
+//      one REDUX.OR + one shared-memory ATOMS.MAX), back-face proof with a per-frame distance bound
+//   B  2 x 3 lockstep footprint for triangles of at most 2 rows x 2 tight columns (separable edge terms)
+//   C  covered FRAGMENTS (not triangles) are parked in a per-warp shared-memory ring: (i0, i1, i2, triangle,
+//      x | y << 16); every 32 of them are emitted with all lanes busy -- gather (x', y', z') of the three
+//      vertices, normal / 1/area / depth / glyph, one 64-bit atomicMin into the key plane
+// Larger triangles: up to 8 x 8 candidates one lane each, beyond that row-band items for k_tail; non-finite or
+// huge triangles go to k_tail's brute-force part.  Bit-exactness: every value is produced by the same
+// round-to-nearest operations in the same order as raster_core.cuh's soup path.
+#pragma once
+#include "kernels.cuh"
+
+namespace sloth {
+
+static constexpr uint32_t T_WARPS = 8;     // warps per block
+#ifndef T_BLOCKS_PER_SM
+#define T_BLOCKS_PER_SM 4
+#endif
+static constexpr uint32_t T_RING = 64;     // per-warp ring of covered fragments (power of two, >= 2 * 32)
+
+struct TRing {
+    uint32_t i0[T_RING], i1[T_RING], i2[T_RING];
+    uint32_t tri[T_RING];
+    uint32_t xy[T_RING];      // x | y << 16
+};
+
+// Emit `count` parked fragments starting at ring position `head`, lane = fragment.
+SLOTH_DEV void t_emit(const FrameParams& p, const Scene& sc, const TRing& wq, uint32_t head, uint32_t count, uint32_t lane,
+                      unsigned long long* __restrict__ keys)
+{
+    if (lane >= count) return;
+    const uint32_t slot = (head + lane) & (T_RING - 1u);
+    const uint32_t i0 = wq.i0[slot], i1 = wq.i1[slot], i2 = wq.i2[slot];
+    const float2 P1 = __ldg(sc.vxy + i0), P2 = __ldg(sc.vxy + i1), P3 = __ldg(sc.vxy + i2);
+    const float z1 = __ldg(sc.vz + i0), z2 = __ldg(sc.vz + i1), z3 = __ldg(sc.vz + i2);
+    const uint32_t tri = wq.tri[slot], xy = wq.xy[slot];
+    Setup s;
+    s.x1 = P1.x; s.y1 = P1.y; s.z1 = z1;
+    s.x2 = P2.x; s.y2 = P2.y; s.z2 = z2;
+    s.x3 = P3.x; s.y3 = P3.y; s.z3 = z3;
+    s.dx0 = sub(s.x3, s.x2); s.dy0 = sub(s.y3, s.y2);
+    s.dx1 = sub(s.x1, s.x3); s.dy1 = sub(s.y1, s.y3);
+    s.dx2 = sub(s.x2, s.x1); s.dy2 = sub(s.y2, s.y1);
+    Shade sh;
+    shade_setup(s, sh);
+    const uint32_t x = xy & 0xFFFFu, y = xy >> 16;
+    const RowC rc = row_setup(s, y);
+    float w0, w1, w2;
+    edge_eval(s, rc, x, w0, w1, w2);
+    emit_fragment(p, s, sh, tri, x, y, w0, w1, w2, keys);
+}
+
+template <bool CHECK_REGULAR, bool BAND>
+__global__ void __launch_bounds__(T_WARPS * 32, T_BLOCKS_PER_SM)
+k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long* __restrict__ keys, const Queues q,
+      const uint32_t rowmax_shared)
+{
+    __shared__ TRing rings[T_WARPS];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    TRing& wq = rings[warp];
+    const uint32_t n_chunks = (p.n_tri + 31u) >> 5;
+    const uint32_t n_warps = gridDim.x * T_WARPS;
+    const uint32_t gw = blockIdx.x * T_WARPS + warp;
+    uint32_t q_head = 0, q_count = 0, nfrag_count = 0, chunks_done = 0;   // warp-uniform
+    const bool do_stamps = p.image && !(p.debug & 2u);
+    uint32_t* const s_rowmax = reinterpret_cast<uint32_t*>(dyn_smem);
+    const uint32_t n_rowmax = ((p.H + 31u) & ~31u) + 64u;
+    uint32_t* const rowmax = rowmax_shared ? s_rowmax : q.rowmax;
+    if (do_stamps && rowmax_shared)
+        for (uint32_t i = threadIdx.x; i < n_rowmax; i += blockDim.x) s_rowmax[i] = 0u;
+    __syncthreads();
+
+    // Band contexts skip a chunk whose bounding sphere cannot reach the band's rows (same test as k_geom3).
+    auto culled = [&](uint32_t idx) -> bool {
+        if (!BAND || !p.cull_on) return false;
+        const float4 s = __ldg(sc.bounds + idx);
+        const float yc = xform_row(p.m + 4, s.x, s.y, s.z);
+        const float R = add(mul(s.w, p.cull_scale), p.cull_pad);
+        return sub(yc, R) >= (float)p.row1 || add(add(yc, R), 2.0f) <= (float)p.krow0;
+    };
+    auto next_live = [&](uint32_t idx) -> uint32_t {   // next chunk of this warp after idx that is not culled
+        do idx += n_warps; while (BAND && idx < n_chunks && culled(idx));
+        return idx;
+    };
+    const uint32_t last = n_chunks ? n_chunks - 1u : 0u;
+    uint32_t c = gw;
+    if (BAND) while (c < n_chunks && culled(c)) c += n_warps;
+    uint32_t c1 = next_live(c);
+    // records: chunk c in r_cur, chunk c1 in r_nxt; gathers of chunk c in A1..A3.  Indices past the end are
+    // clamped to the last chunk (valid memory, results unused) so the pipeline needs no predicates.
+    uint4 r_cur = __ldcs(sc.rec + min(c, last) * 32u + lane);
+    uint4 r_nxt = __ldcs(sc.rec + min(c1, last) * 32u + lane);
+    float2 A1 = __ldg(sc.vxy + r_cur.x), A2 = __ldg(sc.vxy + r_cur.y), A3 = __ldg(sc.vxy + r_cur.z);
+
+    while (c < n_chunks) {
+        const uint32_t t = c * 32u + lane;
+        ++chunks_done;
+        const float x1 = A1.x, y1 = A1.y, x2 = A2.x, y2 = A2.y, x3 = A3.x, y3 = A3.y;
+        const uint32_t i0 = r_cur.x, i1 = r_cur.y, i2 = r_cur.z;
+        // pipeline: gathers of the next chunk, record of the one after
+        A1 = __ldg(sc.vxy + r_nxt.x); A2 = __ldg(sc.vxy + r_nxt.y); A3 = __ldg(sc.vxy + r_nxt.z);
+        const uint32_t c2 = next_live(c1);
+        r_cur = r_nxt;
+        r_nxt = __ldcs(sc.rec + min(c2, last) * 32u + lane);
+
+        // ---- phase A: bounds (Triangle::aabb, rasterizer.rs:58-66) ----------------------------
+        const float mn1 = fminf(y1, fminf(y2, y3)), mx1 = fmaxf(y1, fmaxf(y2, y3));
+        const uint32_t miny = __float2uint_rz(ceilf(fmaxf(mn1, 1.0f)));
+        const uint32_t maxy = __float2uint_rz(ceilf(fminf(mx1, p.hm1)));
+        // padding triangles sit on the sentinel vertex (-1e30): maxy = 0, no rows
+        const bool has_rows = miny < maxy && (!BAND || (miny < p.row1 && maxy + 1u > p.krow0));
+
+        // ---- row stamps (rasterizer.rs:89-91): rowmax[y] = max(c + 1) over chunks c that stamp row y.  The
+        // lanes of a chunk are neighbours on screen: one REDUX.MIN gives the first row, each lane's rows
+        // become bits of a 32-row window, one REDUX.OR, then lane i owns row first + i.
+        const uint32_t sy0 = BAND ? max(miny, p.srow0) : miny, sy1 = BAND ? min(maxy, p.srow1) : maxy;
+        bool tall = false;   // rows outside the window: stamped in the rare block
+        if (do_stamps) {
+            const bool st = has_rows && (!BAND || sy0 < sy1);
+            const uint32_t first = __reduce_min_sync(0xFFFFFFFFu, st ? sy0 : 0xFFFFFFFFu);
+            const uint32_t lo = sy0 - first, n = sy1 - sy0;   // meaningful when st (then n >= 1)
+            const bool fits = st && lo + n <= 32u;
+            tall = st && !fits;
+            const uint32_t m = fits ? (0xFFFFFFFFu >> (32u - n)) << lo : 0u;
+            const uint32_t need = __reduce_or_sync(0xFFFFFFFFu, m);
+            if ((need >> lane) & 1u) atomicMax(rowmax + first + lane, c + 1u);
+        }
+
+        const float mn0 = fminf(x1, fminf(x2, x3)), mx0 = fmaxf(x1, fmaxf(x2, x3));
+        const uint32_t minx = __float2uint_rz(ceilf(fmaxf(mn0, 1.0f)));
+        const uint32_t maxx = __float2uint_rz(ceilf(fminf(mul(mx0, 2.0f), p.wm1)));
+        const bool live = has_rows && minx < maxx;
+        bool regular = true;
+        if (CHECK_REGULAR)
+            regular = in_limit(x1) && in_limit(y1) && in_limit(x2) && in_limit(y2) && in_limit(x3) && in_limit(y3);
+        const float dx0 = sub(x3, x2), dy0 = sub(y3, y2);
+        const float dx1 = sub(x1, x3), dy1 = sub(y1, y3);
+        const float dx2 = sub(x2, x1), dy2 = sub(y2, y1);
+        // back-face proof (backface_proven, kernels.cuh).  Bounded scenes use one distance bound for the whole
+        // frame (p.bf_k = 2^-18 * D_frame, D_frame >= every triangle's D, rounded up on the host): a larger D
+        // only proves fewer triangles.
+        bool back;
+        if (CHECK_REGULAR) {
+            back = backface_proven(p, dx1, dy1, dx2, dy2, mn0, mx0, mn1, mx1);
+        } else {
+            const float area = sub(mul(dy2, dx1), mul(dx2, dy1));
+            const float T = mul(fmaxf(sub(mx0, mn0), sub(mx1, mn1)), p.bf_k);
+            back = T > 1e-30f && area < -T;
+        }
+        const bool cand = live && regular && !back;
+        const uint32_t rows = maxy - miny, span = maxx - minx;
+        // tight width <= 2  <=>  span <= 2 or floor(max_x) <= minx + 1   (see tight_width)
+        const bool foot = cand && rows <= 2u && (span <= 2u || __float2uint_rz(floorf(mx0)) <= minx + 1u);   // tier 1
+        bool beyond = cand && !foot;   // tier 2 / 3: handled in the rare block
+
+        // ---- tier 1: 2 x 3 footprint in registers, lockstep (same evaluation as k_geom3) ------------
+        uint32_t mask = 0;
+        if (__any_sync(0xFFFFFFFFu, foot)) {
+            float cr[2][3], gc[3][3];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float py = (float)(miny + r);
+                cr[r][0] = mul(dx0, sub(py, y2));
+                cr[r][1] = mul(dx1, sub(py, y3));
+                cr[r][2] = mul(dx2, sub(py, y1));
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float px = (float)(minx + k);
+                gc[k][0] = mul(dy0, sub(px, x2));
+                gc[k][1] = mul(dy1, sub(px, x3));
+                gc[k][2] = mul(dy2, sub(px, x1));
+            }
+            uint32_t cov = 0;
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    // regular triangle: no NaN, so "all >= 0" == "none < 0"
+                    const float w0 = sub(cr[r][0], gc[k][0]), w1 = sub(cr[r][1], gc[k][1]), w2 = sub(cr[r][2], gc[k][2]);
+                    if (!(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f)) cov |= 1u << (r * 3 + k);
+                }
+            const uint32_t cm = (1u << min(span, 3u)) - 1u;
+            const uint32_t valid = cm | (rows > 1u ? cm << 3 : 0u);
+            // a row is finished after column 2 if a closing edge (dy >= 0) fails there
+            bool open = false;
+            if (span > 3u) {
+                const bool nd0 = !(dy0 < 0.0f), nd1 = !(dy1 < 0.0f), nd2 = !(dy2 < 0.0f);
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const bool closed = (nd0 && sub(cr[r][0], gc[2][0]) < 0.0f) || (nd1 && sub(cr[r][1], gc[2][1]) < 0.0f) ||
+                                        (nd2 && sub(cr[r][2], gc[2][2]) < 0.0f);
+                    if ((uint32_t)r < rows && !closed) open = true;
+                }
+            }
+            if (foot) {
+                if (open) beyond = true;   // sliver: the rare block hands it to k_tail
+                else mask = cov & valid;
+            }
+        }
+
+        // park one fragment per lane that has one; returns after emitting full groups of 32
+        auto park = [&](bool has, uint32_t x, uint32_t y) {
+            const unsigned who = __ballot_sync(0xFFFFFFFFu, has);
+            if (has) {
+                const uint32_t slot = (q_head + q_count + __popc(who & ((1u << lane) - 1u))) & (T_RING - 1u);
+                wq.i0[slot] = i0; wq.i1[slot] = i1; wq.i2[slot] = i2;
+                wq.tri[slot] = t;
+                wq.xy[slot] = x | (y << 16);
+            }
+            const uint32_t n = __popc(who);
+            q_count += n;
+            nfrag_count += n;
+            if (q_count >= 32u) {
+                __syncwarp();
+                t_emit(p, sc, wq, q_head, 32u, lane, keys);
+                __syncwarp();
+                q_head = (q_head + 32u) & (T_RING - 1u);
+                q_count -= 32u;
+            }
+        };
+
+        // ---- everything uncommon under one vote: tier 2, tier 3 / irregular queues, tall stamps ----
+        if (__any_sync(0xFFFFFFFFu, beyond || tall || (CHECK_REGULAR && live && !regular))) {
+            if (tall)
+                for (uint32_t y = sy0; y < sy1; ++y) atomicMax(rowmax + y, c + 1u);
+            uint32_t tw;
+            {
+                const uint32_t f = __float2uint_rz(floorf(mx0));
+                const uint32_t te = f >= maxx ? maxx : f + 1u;
+                tw = te > minx ? te - minx : 0u;
+            }
+            bool walk = beyond;
+            const bool mid = beyond && !foot && rows <= 8u && tw <= 6u;   // tier 2: up to 8 x 8, one lane each
+            unsigned long long m64 = 0ull;
+            if (mid) {
+                Setup s;
+                s.x1 = x1; s.y1 = y1; s.x2 = x2; s.y2 = y2; s.x3 = x3; s.y3 = y3;
+                s.dx0 = dx0; s.dy0 = dy0; s.dx1 = dx1; s.dy1 = dy1; s.dx2 = dx2; s.dy2 = dy2;
+                unsigned long long m = 0ull;
+                bool open = false;
+                for (uint32_t r = 0; r < rows && !open; ++r) {
+                    const RowC rc = row_setup(s, miny + r);
+                    bool closed = false;
+                    for (uint32_t k = 0; k < 8u && k < span; ++k) {
+                        float w0, w1, w2;
+                        edge_eval(s, rc, minx + k, w0, w1, w2);
+                        if (!(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f)) m |= 1ull << (r * 8u + k);
+                        else if (row_closed(s, w0, w1, w2)) { closed = true; break; }
+                    }
+                    open = !closed && span > 8u;   // candidates remain right of the window
+                }
+                if (!open) { m64 = m; walk = false; }
+            }
+            while (__any_sync(0xFFFFFFFFu, m64 != 0ull)) {   // tier-2 fragments, one per lane and turn
+                const bool has = m64 != 0ull;
+                const uint32_t bit = has ? (uint32_t)__ffsll((long long)m64) - 1u : 0u;
+                m64 &= m64 - 1ull;
+                park(has, minx + (bit & 7u), miny + (bit >> 3));
+            }
+            // tier 3: row-band work items for k_tail, one warp-aggregated atomic
+            const uint32_t walk_items = walk ? (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw) : 0u;
+            const unsigned need = __ballot_sync(0xFFFFFFFFu, walk_items > 0);
+            if (need) {
+                uint32_t wi = walk_items;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t nn = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                    if ((int)lane >= d) wi += nn;
+                }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, wi, 31);
+                unsigned long long old = 0;
+                if (lane == 0)
+                    old = atomicAdd(&q.aux->walk_counter, ((unsigned long long)__popc(need) << ITEM_BITS) | total);
+                old = __shfl_sync(0xFFFFFFFFu, old, 0);
+                if (walk_items > 0) {
+                    const uint32_t slot = (uint32_t)(old >> ITEM_BITS) + __popc(need & ((1u << lane) - 1u));
+                    q.walk_tri[slot] = t;
+                    q.walk_base[slot] = (old & ITEM_MASK) + (wi - walk_items);
+                }
+            }
+            if (CHECK_REGULAR) {
+                const unsigned irr = __ballot_sync(0xFFFFFFFFu, live && !regular);
+                if (irr) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&q.aux->irr_count, (uint32_t)__popc(irr));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (live && !regular) q.irr_tri[base + __popc(irr & ((1u << lane) - 1u))] = t;
+                }
+            }
+        }
+
+        // ---- phase C: park the covered fragments of the 2 x 3 footprint, one per lane and turn ------
+        while (__any_sync(0xFFFFFFFFu, mask != 0u)) {
+            const bool has = mask != 0u;
+            const uint32_t bit = has ? (uint32_t)__ffs((int)mask) - 1u : 0u;
+            mask &= mask - 1u;
+            const uint32_t r = bit >= 3u ? 1u : 0u;
+            park(has, minx + bit - 3u * r, miny + r);
+        }
+
+        c = c1;
+        c1 = c2;
+    }
+    if (q_count) {
+        __syncwarp();
+        t_emit(p, sc, wq, q_head, q_count, lane, keys);
+    }
+    if (do_stamps && rowmax_shared) {   // publish this block's stamps (the probe skips most atomics)
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n_rowmax - 64u; i += blockDim.x) {
+            const uint32_t m = s_rowmax[i];
+            if (m && __ldcg(q.rowmax + i) < m) atomicMax(q.rowmax + i, m);
+        }
+    }
+    if (p.count_frags && lane == 0) {
+        if (nfrag_count) atomicAdd(&q.aux->frag_counter, (unsigned long long)nfrag_count);
+        if (chunks_done) atomicAdd(&q.aux->chunks_done, chunks_done);
+    }
+}
+
+}  // namespace sloth

@@ -14,6 +14,14 @@ import scenes as S
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["soup", "indexed"])
+def geom_path(request, monkeypatch):
+    """Runs the test once per geometry path: SLOTH_PATH pins what every context created inside the test uses
+    (1 = k_geom3 over the soup, 2 = k_xform + k_tri over the deduplicated vertices), whatever AUTO would pick."""
+    monkeypatch.setenv("SLOTH_PATH", "1" if request.param == "soup" else "2")
+    return request.param
+
+
 def gpu_frame(xyz, rgb, s0, W, H, rot, image=True, want_z=True, band=None):
     ctx = rs.Context.blank(image)
     try:
@@ -37,7 +45,7 @@ def assert_same(cells, z, ocells, oz, what):
 
 
 @pytest.mark.parametrize("case", S.golden()["cases"], ids=lambda c: f"{c['scene']}-{c['W']}x{c['H']}")
-def test_bundled_models_match_oracle_and_golden(case):
+def test_bundled_models_match_oracle_and_golden(case, geom_path):
     xyz, rgb, s0 = S.soup(case["scene"])
     rot = oracle.rotation(case["roll"], case["pitch"], case["yaw"])
     ocells, oz, ocnt = oracle.render(xyz, rgb, s0, case["W"], case["H"], rot, image=True, mode=0)
@@ -50,7 +58,7 @@ def test_bundled_models_match_oracle_and_golden(case):
 
 @pytest.mark.parametrize("image", [True, False])
 @pytest.mark.parametrize("kind", ["uniform", "small", "sliver", "collinear", "dup", "axis"])
-def test_fuzz_soups(kind, image):
+def test_fuzz_soups(kind, image, geom_path):
     sizes = [(7, 7), (8, 9), (33, 20), (64, 64), (101, 57), (160, 80), (199, 200), (2, 2), (3, 1), (1, 5)]
     for seed in range(40):
         n = 1 + (seed * 7) % 64
@@ -62,7 +70,7 @@ def test_fuzz_soups(kind, image):
         assert_same(cells, z, ocells, oz, f"{kind} seed={seed} n={n} {W}x{H} image={image}")
 
 
-def test_non_finite_and_huge_coordinates():
+def test_non_finite_and_huge_coordinates(geom_path):
     xyz, rgb, s0 = meshes.random_soup(3, 24)
     xyz = xyz.copy()
     xyz[1, 2] = np.nan
@@ -79,7 +87,7 @@ def test_non_finite_and_huge_coordinates():
         assert_same(cells, z, ocells, oz, f"nonfinite {W}x{H}")
 
 
-def test_degenerate_scene_scale():
+def test_degenerate_scene_scale(geom_path):
     xyz, rgb, _ = meshes.random_soup(5, 16)
     rot = oracle.rotation(0.0, 3.0, 0.0)
     for s0 in [0.0, np.inf, np.nan, 1e-30]:
@@ -88,7 +96,7 @@ def test_degenerate_scene_scale():
         assert_same(cells, z, ocells, oz, f"scale0={s0}")
 
 
-def test_empty_scene_and_tiny_frames():
+def test_empty_scene_and_tiny_frames(geom_path):
     rot = oracle.rotation(0.0, 3.0, 0.0)
     e_xyz, e_rgb = np.zeros((0, 9), np.float32), np.zeros((0, 3), np.uint8)
     for (W, H) in [(1, 1), (2, 3), (80, 40)]:
@@ -97,7 +105,7 @@ def test_empty_scene_and_tiny_frames():
         assert_same(cells, z, ocells, oz, f"empty {W}x{H}")
 
 
-def test_icosphere_small_frequencies():
+def test_icosphere_small_frequencies(geom_path):
     for f, (W, H) in [(4, (80, 40)), (24, (160, 80)), (64, (320, 200))]:
         xyz, rgb, s0 = meshes.icosphere(f)
         for k in range(3):
@@ -108,7 +116,7 @@ def test_icosphere_small_frequencies():
             assert st["fragments"] == ocnt["covered"]
 
 
-def test_custom_shader_table():
+def test_custom_shader_table(geom_path):
     xyz, rgb, s0 = S.soup("suzy")
     rot = oracle.rotation(0.0, S.PI, 0.0)
     thr = np.array([0.1, 0.15, 0.35, 0.5, 0.55, 0.6, 0.85, 0.95, 2.0], np.float32)
@@ -123,7 +131,7 @@ def test_custom_shader_table():
     assert_same(cells, z, ocells, oz, "custom shader")
 
 
-def test_row_bands_reassemble_to_the_whole_frame():
+def test_row_bands_reassemble_to_the_whole_frame(geom_path):
     xyz, rgb, s0 = S.soup("pikachu")
     pitches = oracle.turntable(0.0, 360)
     for (W, H, nb) in [(160, 80, 4), (161, 83, 3), (80, 40, 8)]:
@@ -140,7 +148,7 @@ def test_row_bands_reassemble_to_the_whole_frame():
         assert bad.size == 0, f"bands {W}x{H}/{nb}: {bad.size} cells differ, first {bad[:8]}"
 
 
-def test_row_bands_with_chunk_culling_on_a_large_scene():
+def test_row_bands_with_chunk_culling_on_a_large_scene(geom_path):
     """Band contexts skip whole chunks of 32 triangles by bounding sphere: many thin bands over a dense mesh
     (most chunks are culled in every band), rotations that tilt the mesh, even and odd widths, and the cull
     switched off (SLOTH_DEBUG=4 is read at context creation) must all give the whole frame."""
@@ -164,7 +172,7 @@ def test_row_bands_with_chunk_culling_on_a_large_scene():
     assert np.array_equal(gpu_frame(xyz, rgb, s0, 333, 250, oracle.rotation(1.1, 0.4, 2.0))[0], ocells)
 
 
-def test_batch_equals_single_frames_and_is_deterministic():
+def test_batch_equals_single_frames_and_is_deterministic(geom_path):
     xyz, rgb, s0 = S.soup("pikachu")
     pitches = oracle.turntable(0.0, 12)
     rots = np.stack([oracle.rotation(0.0, p, 0.0) for p in pitches])
@@ -266,7 +274,7 @@ def test_ipc_helpers_round_trip():
     ctx.close()
 
 
-def test_newline_stamp_vs_wrapped_fragment_order():
+def test_newline_stamp_vs_wrapped_fragment_order(geom_path):
     """A fragment that wraps onto column 0/1 of a stamped row (2x == W or W+1): the cell shows the
     fragment only if its triangle is later than every triangle stamping that row."""
     rot = np.eye(4, dtype=np.float32).reshape(16)
@@ -286,7 +294,7 @@ def test_newline_stamp_vs_wrapped_fragment_order():
     assert hits > 0   # the exact same-chunk check was exercised
 
 
-def test_one_column_frames_keep_their_newline_stamps():
+def test_one_column_frames_keep_their_newline_stamps(geom_path):
     """W == 1: no x candidate exists, but the newline stamp of row y is cell y*W+1 = (row y+1, column 0)
     (found by the hypothesis fuzz: nine degenerate triangles and one that spans a row, 1x4)."""
     tris = np.zeros((10, 9), np.float32)
@@ -314,7 +322,7 @@ def test_one_column_frames_keep_their_newline_stamps():
             assert np.array_equal(banded, ocells), f"1x{H} seed {seed} in {nb} bands"
 
 
-def test_tall_frame_uses_global_row_stamps():
+def test_tall_frame_uses_global_row_stamps(geom_path):
     xyz, rgb, s0 = S.soup("suzy")
     rot = oracle.rotation(0.0, S.PI, 0.0)
     W, H = 16, 9000   # H > 8192: the row-stamp array no longer fits in shared memory
@@ -323,7 +331,7 @@ def test_tall_frame_uses_global_row_stamps():
     assert_same(cells, z, ocells, oz, "tall frame")
 
 
-def test_device_batch_overlap_equals_single_frames():
+def test_device_batch_overlap_equals_single_frames(geom_path):
     """sloth_render_device_batch (geometry k+1 overlapping resolve k on two streams) == frame by frame."""
     import torch
     xyz, rgb, s0 = meshes.icosphere(40)
@@ -454,7 +462,7 @@ _coord = st.one_of(
        W=st.integers(min_value=1, max_value=70), H=st.integers(min_value=1, max_value=40),
        angles=st.tuples(st.floats(-7, 7, width=32), st.floats(-7, 7, width=32), st.floats(-7, 7, width=32)),
        image=st.booleans(), s0=st.sampled_from([1.0, 0.7, 2.5, 0.0]))
-def test_hypothesis_fuzz_gpu_vs_oracle(tris, W, H, angles, image, s0):
+def test_hypothesis_fuzz_gpu_vs_oracle(tris, W, H, angles, image, s0, geom_path):
     """Arbitrary small soups incl. NaN / inf / denormal / huge coordinates, 1-cell frames, odd widths."""
     xyz = np.array(tris, np.float32)
     rgb = (np.arange(xyz.shape[0] * 3, dtype=np.int64) * 37 % 256).astype(np.uint8).reshape(-1, 3)
@@ -463,3 +471,52 @@ def test_hypothesis_fuzz_gpu_vs_oracle(tris, W, H, angles, image, s0):
     cells, z, st_ = gpu_frame(xyz, rgb, np.float32(s0), W, H, rot, image=image)
     assert_same(cells, z, ocells, oz, "hypothesis")
     assert st_["fragments"] == ocnt["covered"]
+
+
+def test_indexed_scene_dedupes_by_bit_pattern_and_auto_picks_the_path():
+    """sloth_scene_set deduplicates corners (index.cuh): an icosphere of frequency f has 10 f^2 + 2 distinct vertices;
+    AUTO takes the per-vertex path for shared meshes and keeps the soup path for soups without sharing;
+    sloth_scene_set_indexed (positions + indices, geometry.rs:99-107) ends in the same frames."""
+    f = 24
+    xyz, rgb, s0 = meshes.icosphere(f)
+    W, H = 200, 100
+    rot = oracle.rotation(0.2, np.float32(np.pi) + 0.4, 0.1)
+    ocells, oz, _ = oracle.render(xyz, rgb, s0, W, H, rot, image=True, mode=0)
+    ctx = rs.Context.blank(True)
+    try:
+        ctx.set_scene(xyz, rgb, s0)
+        ctx.resize(W, H)
+        st = ctx.stats()
+        assert st["geom_path"] == rs.PATH_INDEXED and st["n_vert"] == 10 * f * f + 2
+        cells, z = ctx.render(rot, want_z=True)
+        assert_same(cells, z, ocells, oz, "icosphere, AUTO -> indexed")
+        # the caller's own indexing: unique rows of the soup + inverse map
+        corners = np.ascontiguousarray(xyz.reshape(-1, 3))
+        keys = corners.view(np.uint32).astype(np.uint64)
+        packed = (keys[:, 0] << np.uint64(40)) ^ (keys[:, 1] << np.uint64(20)) ^ keys[:, 2]
+        _, first, inv = np.unique(packed, return_index=True, return_inverse=True)
+        assert np.array_equal(corners[first][inv].view(np.uint32), corners.view(np.uint32)), "test hash collided"
+        ctx.set_scene_indexed(corners[first], inv.reshape(-1, 3), rgb, s0)
+        assert ctx.stats()["n_vert"] == 10 * f * f + 2
+        cells2, z2 = ctx.render(rot, want_z=True)
+        assert_same(cells2, z2, ocells, oz, "icosphere, set_scene_indexed")
+        dxyz, drgb, _ = ctx.scene()
+        assert np.array_equal(dxyz.view(np.uint32), xyz.view(np.uint32)) and np.array_equal(drgb, rgb)
+        with pytest.raises(rs.SlothError) as e:
+            bad = inv.reshape(-1, 3).copy()
+            bad[7, 1] = len(first)
+            ctx.set_scene_indexed(corners[first], bad, rgb, s0)
+        assert e.value.code == rs.SLOTH_E_ARG
+        # -0.0 and +0.0 are different vertices (bit patterns), NaN payloads too: nothing is merged by value
+        tri = np.array([[0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0, 0.0],
+                        [-0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0, 0.0]], np.float32)
+        ctx.set_path(rs.PATH_INDEXED)
+        ctx.set_scene(tri, rgb[:2], 1.0)
+        assert ctx.stats()["n_vert"] == 4
+        # a soup without sharing stays on the soup path under AUTO
+        ctx.set_path(rs.PATH_AUTO)
+        sxyz, srgb, ss0 = meshes.random_soup(3, 500)
+        ctx.set_scene(sxyz, srgb, ss0)
+        assert ctx.stats()["geom_path"] == rs.PATH_SOUP and ctx.stats()["n_vert"] == 0
+    finally:
+        ctx.close()
