@@ -211,6 +211,8 @@ typedef struct sloth_stats {
     uint32_t n_vert;           /* unique vertices of the resident scene (0 when it renders through the soup path) */
     uint32_t geom_path;        /* SLOTH_PATH_SOUP or SLOTH_PATH_INDEXED: what the resident scene uses */
     float xform_ms;            /* per-vertex transform kernel of the last sloth_render when timing is on (indexed path) */
+    uint64_t l2_window_bytes;  /* bytes of transformed vertices kept L2-resident by an access-policy window (0 = none) */
+    uint64_t l2_persist_max;   /* the device's persisting-L2 set-aside limit */
 } sloth_stats;
 
 SLOTH_API int sloth_stats_get(sloth_ctx *ctx, sloth_stats *out);

@@ -2,7 +2,7 @@
 ncu report, per `units` (default 313290 = 32-triangle chunks of the bench scene)."""
 import csv, io, subprocess, sys, collections
 rep = sys.argv[1]; units = float(sys.argv[2]) if len(sys.argv) > 2 else 313290.0
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + __import__("os").environ.get("NCU_FILTER", "").split(), capture_output=True, text=True).stdout
 lines = src.splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
 rows = list(csv.reader(io.StringIO("\n".join(lines[start:]))))

@@ -3,7 +3,7 @@ with the same execution count (cheap way to see which phase of a kernel issues h
 import csv, subprocess, io, sys
 rep = sys.argv[1]
 thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.004
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + __import__("os").environ.get("NCU_FILTER", "").split(), capture_output=True, text=True).stdout
 lines = src.splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
 rows = list(csv.reader(io.StringIO("\n".join(lines[start:]))))

@@ -4,7 +4,7 @@ import csv, subprocess, sys, io
 
 rep = sys.argv[1]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + __import__("os").environ.get("NCU_FILTER", "").split(), capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct",
@@ -22,7 +22,7 @@ for r in rows[2:]:
     for h, u, v in zip(hdr, units, r):
         if any(h.startswith(w.strip()) for w in WANT) and "per_second" not in h and "pct_of_peak_sustained_elapsed" not in h.replace("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "").replace("sm__throughput.avg.pct_of_peak_sustained_elapsed", ""):
             print(f"  {h} [{u}] = {v}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + __import__("os").environ.get("NCU_FILTER", "").split(), capture_output=True, text=True).stdout
 lines = src.splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
 rows = list(csv.reader(io.StringIO("\n".join(lines[start:]))))

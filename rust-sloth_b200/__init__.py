@@ -73,6 +73,7 @@ class Stats(C.Structure):
         ("chunks_processed", C.c_uint32),
         ("load_read_ms", C.c_float), ("load_parse_ms", C.c_float), ("load_commit_ms", C.c_float),
         ("n_vert", C.c_uint32), ("geom_path", C.c_uint32), ("xform_ms", C.c_float),
+        ("l2_window_bytes", C.c_uint64), ("l2_persist_max", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

@@ -105,6 +105,9 @@ struct sloth_ctx {
     float2* vxy = nullptr;            // [n_vert + 1], rewritten every frame
     float* vz = nullptr;
     uint32_t tri_blocks_per_sm = T_BLOCKS_PER_SM;   // SLOTH_TGRID overrides (profiling)
+    uint32_t pf_chunks = 0;           // SLOTH_PF: L2 prefetch distance of k_tri's record stream (measured: hurts, off)
+    size_t l2_persist_max = 0, l2_window_max = 0;   // device limits of the persisting-L2 set-aside / access window
+    size_t l2_window_bytes = 0;       // bytes of (vxy, vz) currently covered by the persisting window
 
     // frame state
     uint32_t W = 0, H = 0;
@@ -245,6 +248,7 @@ void build_params(const sloth_ctx* c, const float rot[16], FrameParams& p)
         const float k = (float)(D * 3.814697265625e-06 * 1.0001);   // 2^-18 D, rounded up
         if (std::isfinite(k)) p.bf_k = std::nextafterf(k, std::numeric_limits<float>::infinity());
     }
+    p.pf_chunks = c->pf_chunks;
     p.cull_on = 0u;
     p.cull_scale = p.cull_pad = 0.0f;
     if (band && c->scene_clean && !(c->debug & 4u)) {
@@ -290,10 +294,14 @@ int apply_carveout(sloth_ctx* c, int pct)
     CU(cudaFuncSetAttribute(k_resolve_odd, a, pct));
     CU(cudaFuncSetAttribute(k_clear_keys_odd, a, pct));
     CU(cudaFuncSetAttribute(k_xform, a, pct));
-    CU(cudaFuncSetAttribute(k_tri<false, false>, a, pct));
-    CU(cudaFuncSetAttribute(k_tri<false, true>, a, pct));
-    CU(cudaFuncSetAttribute(k_tri<true, false>, a, pct));
-    CU(cudaFuncSetAttribute(k_tri<true, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<false, false, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<false, true, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<true, false, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<true, true, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<false, false, false>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<false, true, false>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<true, false, false>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<true, true, false>, a, pct));
     CU(cudaFuncSetAttribute(k_geom3<false, false, false>, a, pct));
     CU(cudaFuncSetAttribute(k_geom3<false, true, false>, a, pct));
     CU(cudaFuncSetAttribute(k_geom3<true, false, false>, a, pct));
@@ -316,11 +324,16 @@ int enqueue_geometry_indexed(sloth_ctx* c, const FrameParams& p, const Scene& sc
     // a clean scene under a bounded matrix cannot produce |x'|,|y'| > 2^40: skip the per-triangle test
     bool bounded = c->scene_clean;
     for (int i = 0; i < 8; ++i) bounded = bounded && std::fabs(p.m[i]) <= 131072.0f;
-    const uint32_t rowmax_shared = c->rowmax_bytes <= 33024u ? 1u : 0u;
+    const bool rowmax_shared = c->rowmax_bytes <= 33024u;
     const size_t dyn = rowmax_shared ? c->rowmax_bytes : 0;
     const bool band_mode = c->row1 != 0;
-    void (*kern)(FrameParams, Scene, unsigned long long*, Queues, uint32_t) =
-        bounded ? (band_mode ? k_tri<false, true> : k_tri<false, false>) : (band_mode ? k_tri<true, true> : k_tri<true, false>);
+    void (*kern)(FrameParams, Scene, unsigned long long*, Queues);
+    if (rowmax_shared)
+        kern = bounded ? (band_mode ? k_tri<false, true, true> : k_tri<false, false, true>)
+                       : (band_mode ? k_tri<true, true, true> : k_tri<true, false, true>);
+    else
+        kern = bounded ? (band_mode ? k_tri<false, true, false> : k_tri<false, false, false>)
+                       : (band_mode ? k_tri<true, true, false> : k_tri<true, false, false>);
     {
         const size_t per_block = sizeof(TRing) * T_WARPS + dyn + 1024;
         int pct = (int)((per_block * bps * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
@@ -331,7 +344,7 @@ int enqueue_geometry_indexed(sloth_ctx* c, const FrameParams& p, const Scene& sc
     const float* px = c->sc_pos;
     k_xform<<<(c->n_vert + 1 + 255) / 256, 256, 0, st>>>(p, px, px + c->pos_stride, px + 2 * c->pos_stride, c->n_vert, c->vxy, c->vz);
     if (kt) CU(cudaEventRecord(c->ev[EV_XFORM], st));
-    kern<<<grid, T_WARPS * 32, dyn, st>>>(p, sc, c->keys[set], q, rowmax_shared);
+    kern<<<grid, T_WARPS * 32, dyn, st>>>(p, sc, c->keys[set], q);
     c->launches += 2;
     if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
     return SLOTH_OK;
@@ -538,8 +551,16 @@ int check_ready(sloth_ctx* c)
 
 void free_index(sloth_ctx* c)
 {
-    cudaFree(c->sc_pos); cudaFree(c->sc_rec); cudaFree(c->vxy); cudaFree(c->vz);
+    cudaFree(c->sc_pos); cudaFree(c->sc_rec); cudaFree(c->vxy);   // vz lives in vxy's allocation
     c->sc_pos = nullptr; c->sc_rec = nullptr; c->vxy = nullptr; c->vz = nullptr;
+    if (c->l2_window_bytes) {   // drop the residency window of the transformed vertices
+        cudaStreamAttrValue attr;
+        std::memset(&attr, 0, sizeof attr);
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaCtxResetPersistingL2Cache();
+        c->l2_window_bytes = 0;
+    }
     c->indexed = false;
     c->n_vert = 0;
     c->pos_stride = 0;
@@ -552,9 +573,33 @@ int alloc_index(sloth_ctx* c, size_t n_vert, size_t n_tri)
     const size_t n_padded = (n_tri + 31) & ~(size_t)31;
     CU(cudaMalloc(&c->sc_pos, 3 * c->pos_stride * sizeof(float)));
     CU(cudaMalloc(&c->sc_rec, std::max<size_t>(n_padded, 32) * sizeof(uint4)));
-    CU(cudaMalloc(&c->vxy, (n_vert + 1) * sizeof(float2)));
-    CU(cudaMalloc(&c->vz, (n_vert + 1) * sizeof(float)));
+    // (x', y') and z' of every vertex in one allocation, so that one L2 access-policy window covers both
+    const size_t xy_bytes = ((n_vert + 1) * sizeof(float2) + 255) & ~(size_t)255;
+    const size_t all_bytes = xy_bytes + (n_vert + 1) * sizeof(float);
+    CU(cudaMalloc(&c->vxy, all_bytes));
+    c->vz = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(c->vxy) + xy_bytes);
     c->n_vert = (uint32_t)n_vert;
+    // Keep the transformed vertices resident in L2 between k_xform (writes them) and k_tri (gathers them): the
+    // triangle records stream past them at 16 B/triangle and would otherwise push half of them out to HBM
+    // (ncu: 50 % of the gather sectors missed L2).  Persisting lines live in a set-aside part of L2; when the
+    // set-aside is smaller than the window, hitRatio keeps only that fraction persisting (no thrash).
+    c->l2_window_bytes = 0;
+    if (c->l2_persist_max && c->l2_window_max && all_bytes >= (1u << 20) && !(c->debug & 32u)) {
+        const size_t window = std::min(all_bytes, c->l2_window_max);
+        const size_t carve = std::min(window, c->l2_persist_max);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+            cudaStreamAttrValue attr;
+            std::memset(&attr, 0, sizeof attr);
+            attr.accessPolicyWindow.base_ptr = c->vxy;
+            attr.accessPolicyWindow.num_bytes = window;
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess)
+                c->l2_window_bytes = window;
+        }
+        cudaGetLastError();   // residency control is an optimisation: never fatal
+    }
     return SLOTH_OK;
 }
 
@@ -698,6 +743,8 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    c->l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
+    c->l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
     if (const char* g = std::getenv("SLOTH_DEBUG")) c->debug = (uint32_t)std::atoi(g);
     if (const char* g = std::getenv("SLOTH_TMA")) c->tma_feed = std::atoi(g) != 0;
     if (const char* g = std::getenv("SLOTH_CARVEOUT")) c->carveout_override = std::atoi(g);   // profiling knob
@@ -705,6 +752,7 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     if (const char* g = std::getenv("SLOTH_BATCH")) c->batch_max = (uint32_t)std::min(16, std::max(1, std::atoi(g)));
     if (const char* g = std::getenv("SLOTH_GRID")) c->geom_blocks_per_sm = (uint32_t)std::max(1, std::atoi(g));
     if (const char* g = std::getenv("SLOTH_TGRID")) c->tri_blocks_per_sm = (uint32_t)std::min((int)T_BLOCKS_PER_SM, std::max(1, std::atoi(g)));
+    if (const char* g = std::getenv("SLOTH_PF")) c->pf_chunks = (uint32_t)std::min(64, std::max(0, std::atoi(g)));
     if (const char* g = std::getenv("SLOTH_PATH")) c->path_pref = std::min(2, std::max(0, std::atoi(g)));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -1191,6 +1239,8 @@ int sloth_stats_get(sloth_ctx* c, sloth_stats* out)
     out->load_read_ms = c->load_ms[0];
     out->load_parse_ms = c->load_ms[1];
     out->load_commit_ms = c->load_ms[2];
+    out->l2_window_bytes = (uint64_t)c->l2_window_bytes;
+    out->l2_persist_max = (uint64_t)c->l2_persist_max;
     out->n_vert = c->indexed ? c->n_vert : 0u;
     out->geom_path = c->indexed ? (uint32_t)SLOTH_PATH_INDEXED : (uint32_t)SLOTH_PATH_SOUP;
     if (c->sized && c->aux_region[c->last_set]) {

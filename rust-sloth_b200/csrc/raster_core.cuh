@@ -38,7 +38,8 @@ struct FrameParams {
     uint32_t n_tri;
     uint32_t image;    // Context.image
     uint32_t count_frags;
-    uint32_t debug;    // profiling experiments only (SLOTH_DEBUG): 1 = skip key atomics, 2 = skip row stamps
+    uint32_t debug;    // profiling experiments only (SLOTH_DEBUG): 1 = skip key atomics, 2 = skip row stamps, 8 = k_tri parks but
+                       // never emits, 16 = k_tri stops every chunk after the back-face proof
     char glyph[12];    // 10 glyphs (+pad)
     // band contexts: whole chunks of 32 triangles are skipped when their bounding sphere (Scene::bounds) cannot
     // reach the band's rows.  cull_scale = |row 1 of M| (rounded up), cull_pad = bound on the rounding error of
@@ -48,6 +49,7 @@ struct FrameParams {
     // indexed path (k_tri), bounded scenes only: 2^-18 * D_frame, D_frame >= the distance bound D of every
     // triangle's back-face proof (backface_proven), rounded up on the host
     float bf_k;
+    uint32_t pf_chunks;   // k_tri: L2 prefetch distance of the record stream in chunks per warp (SLOTH_PF, 0 = off)
 };
 
 // Resident scene: 40 B per triangle in four coalesced streams; the geometry kernels read the first

@@ -28,21 +28,21 @@ static constexpr uint32_t T_WARPS = 8;     // warps per block
 static constexpr uint32_t T_RING = 64;     // per-warp ring of covered fragments (power of two, >= 2 * 32)
 
 struct TRing {
-    uint32_t i0[T_RING], i1[T_RING], i2[T_RING];
     uint32_t tri[T_RING];
     uint32_t xy[T_RING];      // x | y << 16
 };
 
-// Emit `count` parked fragments starting at ring position `head`, lane = fragment.
+// Emit `count` parked fragments starting at ring position `head`, lane = fragment: the triangle's record and its
+// three transformed vertices are gathered again (L1 / L2 hits: the warp touched them a chunk or two ago).
 SLOTH_DEV void t_emit(const FrameParams& p, const Scene& sc, const TRing& wq, uint32_t head, uint32_t count, uint32_t lane,
                       unsigned long long* __restrict__ keys)
 {
-    if (lane >= count) return;
+    if (lane >= count || (p.debug & 8u)) return;
     const uint32_t slot = (head + lane) & (T_RING - 1u);
-    const uint32_t i0 = wq.i0[slot], i1 = wq.i1[slot], i2 = wq.i2[slot];
-    const float2 P1 = __ldg(sc.vxy + i0), P2 = __ldg(sc.vxy + i1), P3 = __ldg(sc.vxy + i2);
-    const float z1 = __ldg(sc.vz + i0), z2 = __ldg(sc.vz + i1), z3 = __ldg(sc.vz + i2);
     const uint32_t tri = wq.tri[slot], xy = wq.xy[slot];
+    const uint4 r = __ldg(sc.rec + tri);
+    const float2 P1 = __ldg(sc.vxy + r.x), P2 = __ldg(sc.vxy + r.y), P3 = __ldg(sc.vxy + r.z);
+    const float z1 = __ldg(sc.vz + r.x), z2 = __ldg(sc.vz + r.y), z3 = __ldg(sc.vz + r.z);
     Setup s;
     s.x1 = P1.x; s.y1 = P1.y; s.z1 = z1;
     s.x2 = P2.x; s.y2 = P2.y; s.z2 = z2;
@@ -59,13 +59,14 @@ SLOTH_DEV void t_emit(const FrameParams& p, const Scene& sc, const TRing& wq, ui
     emit_fragment(p, s, sh, tri, x, y, w0, w1, w2, keys);
 }
 
-template <bool CHECK_REGULAR, bool BAND>
+// ROWMAX_SHARED: the per-block copy of rowmax lives in dynamic shared memory (frames up to ~8 K rows), so the row
+// stamps are shared-memory atomics (ATOMS) instead of generic ones.
+template <bool CHECK_REGULAR, bool BAND, bool ROWMAX_SHARED>
 __global__ void __launch_bounds__(T_WARPS * 32, T_BLOCKS_PER_SM)
-k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long* __restrict__ keys, const Queues q,
-      const uint32_t rowmax_shared)
+k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long* __restrict__ keys, const Queues q)
 {
     __shared__ TRing rings[T_WARPS];
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    extern __shared__ __align__(16) uint32_t s_rowmax[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     TRing& wq = rings[warp];
     const uint32_t n_chunks = (p.n_tri + 31u) >> 5;
@@ -73,12 +74,14 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     const uint32_t gw = blockIdx.x * T_WARPS + warp;
     uint32_t q_head = 0, q_count = 0, nfrag_count = 0, chunks_done = 0;   // warp-uniform
     const bool do_stamps = p.image && !(p.debug & 2u);
-    uint32_t* const s_rowmax = reinterpret_cast<uint32_t*>(dyn_smem);
     const uint32_t n_rowmax = ((p.H + 31u) & ~31u) + 64u;
-    uint32_t* const rowmax = rowmax_shared ? s_rowmax : q.rowmax;
-    if (do_stamps && rowmax_shared)
+    if (ROWMAX_SHARED && do_stamps)
         for (uint32_t i = threadIdx.x; i < n_rowmax; i += blockDim.x) s_rowmax[i] = 0u;
     __syncthreads();
+    auto stamp = [&](uint32_t row, uint32_t value) {
+        if (ROWMAX_SHARED) atomicMax(s_rowmax + row, value);
+        else atomicMax(q.rowmax + row, value);
+    };
 
     // Band contexts skip a chunk whose bounding sphere cannot reach the band's rows (same test as k_geom3).
     auto culled = [&](uint32_t idx) -> bool {
@@ -93,25 +96,36 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
         return idx;
     };
     const uint32_t last = n_chunks ? n_chunks - 1u : 0u;
-    uint32_t c = gw;
-    if (BAND) while (c < n_chunks && culled(c)) c += n_warps;
-    uint32_t c1 = next_live(c);
-    // records: chunk c in r_cur, chunk c1 in r_nxt; gathers of chunk c in A1..A3.  Indices past the end are
-    // clamped to the last chunk (valid memory, results unused) so the pipeline needs no predicates.
-    uint4 r_cur = __ldcs(sc.rec + min(c, last) * 32u + lane);
-    uint4 r_nxt = __ldcs(sc.rec + min(c1, last) * 32u + lane);
-    float2 A1 = __ldg(sc.vxy + r_cur.x), A2 = __ldg(sc.vxy + r_cur.y), A3 = __ldg(sc.vxy + r_cur.z);
+    const uint32_t pf_dist = p.pf_chunks * n_warps;   // L2 prefetch distance of the record stream (0 = off)
+    // Software pipeline, two chunks deep, without register rotation: the loop body exists twice, once per
+    // coordinate set (A, B).  While set A's chunk is computed, set B's gathers (the chunk after it) are in flight;
+    // as soon as A's coordinates are dead the gathers of the chunk after B's are issued into A, and the record
+    // register is refilled with the record of the chunk after that.  Chunk indices past the end are clamped to
+    // the last chunk (valid memory, results unused).
+    // A record is read as 8 + 4 bytes: a 16-byte load would leave its unused last word to the register allocator,
+    // which hands it to the next instruction -- and that instruction then waits for the whole load.
+    struct Rec { uint32_t x, y, z; };
+    auto load_rec = [&](uint32_t chunk) -> Rec {
+        const uint4* r = sc.rec + min(chunk, last) * 32u + lane;
+        const uint2 a = __ldcs(reinterpret_cast<const uint2*>(r));
+        const uint32_t b = __ldcs(reinterpret_cast<const uint32_t*>(r) + 2);
+        return Rec{a.x, a.y, b};
+    };
+    uint32_t cA = gw;
+    if (BAND) while (cA < n_chunks && culled(cA)) cA += n_warps;
+    uint32_t cB = next_live(cA);
+    uint32_t cN = next_live(cB);   // the chunk whose record is in rn
+    Rec rn = load_rec(cA);
+    float2 A1 = __ldg(sc.vxy + rn.x), A2 = __ldg(sc.vxy + rn.y), A3 = __ldg(sc.vxy + rn.z);
+    rn = load_rec(cB);
+    float2 B1 = __ldg(sc.vxy + rn.x), B2 = __ldg(sc.vxy + rn.y), B3 = __ldg(sc.vxy + rn.z);
+    rn = load_rec(cN);
 
-    while (c < n_chunks) {
+    auto body = [&](float2& P1, float2& P2, float2& P3, uint32_t& c_set) {
+        const uint32_t c = c_set;
         const uint32_t t = c * 32u + lane;
-        ++chunks_done;
-        const float x1 = A1.x, y1 = A1.y, x2 = A2.x, y2 = A2.y, x3 = A3.x, y3 = A3.y;
-        const uint32_t i0 = r_cur.x, i1 = r_cur.y, i2 = r_cur.z;
-        // pipeline: gathers of the next chunk, record of the one after
-        A1 = __ldg(sc.vxy + r_nxt.x); A2 = __ldg(sc.vxy + r_nxt.y); A3 = __ldg(sc.vxy + r_nxt.z);
-        const uint32_t c2 = next_live(c1);
-        r_cur = r_nxt;
-        r_nxt = __ldcs(sc.rec + min(c2, last) * 32u + lane);
+        if (p.count_frags) ++chunks_done;
+        const float x1 = P1.x, y1 = P1.y, x2 = P2.x, y2 = P2.y, x3 = P3.x, y3 = P3.y;
 
         // ---- phase A: bounds (Triangle::aabb, rasterizer.rs:58-66) ----------------------------
         const float mn1 = fminf(y1, fminf(y2, y3)), mx1 = fmaxf(y1, fmaxf(y2, y3));
@@ -133,22 +147,18 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
             tall = st && !fits;
             const uint32_t m = fits ? (0xFFFFFFFFu >> (32u - n)) << lo : 0u;
             const uint32_t need = __reduce_or_sync(0xFFFFFFFFu, m);
-            if ((need >> lane) & 1u) atomicMax(rowmax + first + lane, c + 1u);
+            if ((need >> lane) & 1u) stamp(first + lane, c + 1u);
         }
 
+        // ---- back-face proof (backface_proven, kernels.cuh).  Bounded scenes use one distance bound for the
+        // whole frame (p.bf_k = 2^-18 * D_frame, D_frame >= every triangle's D, rounded up on the host): a
+        // larger D only proves fewer triangles.
         const float mn0 = fminf(x1, fminf(x2, x3)), mx0 = fmaxf(x1, fmaxf(x2, x3));
-        const uint32_t minx = __float2uint_rz(ceilf(fmaxf(mn0, 1.0f)));
-        const uint32_t maxx = __float2uint_rz(ceilf(fminf(mul(mx0, 2.0f), p.wm1)));
-        const bool live = has_rows && minx < maxx;
+        const float dx1 = sub(x1, x3), dy1 = sub(y1, y3);
+        const float dx2 = sub(x2, x1), dy2 = sub(y2, y1);
         bool regular = true;
         if (CHECK_REGULAR)
             regular = in_limit(x1) && in_limit(y1) && in_limit(x2) && in_limit(y2) && in_limit(x3) && in_limit(y3);
-        const float dx0 = sub(x3, x2), dy0 = sub(y3, y2);
-        const float dx1 = sub(x1, x3), dy1 = sub(y1, y3);
-        const float dx2 = sub(x2, x1), dy2 = sub(y2, y1);
-        // back-face proof (backface_proven, kernels.cuh).  Bounded scenes use one distance bound for the whole
-        // frame (p.bf_k = 2^-18 * D_frame, D_frame >= every triangle's D, rounded up on the host): a larger D
-        // only proves fewer triangles.
         bool back;
         if (CHECK_REGULAR) {
             back = backface_proven(p, dx1, dy1, dx2, dy2, mn0, mx0, mn1, mx1);
@@ -157,70 +167,175 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
             const float T = mul(fmaxf(sub(mx0, mn0), sub(mx1, mn1)), p.bf_k);
             back = T > 1e-30f && area < -T;
         }
-        const bool cand = live && regular && !back;
-        const uint32_t rows = maxy - miny, span = maxx - minx;
-        // tight width <= 2  <=>  span <= 2 or floor(max_x) <= minx + 1   (see tight_width)
-        const bool foot = cand && rows <= 2u && (span <= 2u || __float2uint_rz(floorf(mx0)) <= minx + 1u);   // tier 1
-        bool beyond = cand && !foot;   // tier 2 / 3: handled in the rare block
+        // chunks on the far side of a closed mesh end here (after the stamps); so do empty ones
+        const bool maybe = has_rows && (CHECK_REGULAR ? (!regular || !back) : !back) && !(p.debug & 16u);
+        uint32_t mask = 0, minx = 0;
+        if (__any_sync(0xFFFFFFFFu, maybe || tall)) {
+            minx = __float2uint_rz(ceilf(fmaxf(mn0, 1.0f)));
+            const uint32_t maxx = __float2uint_rz(ceilf(fminf(mul(mx0, 2.0f), p.wm1)));
+            const bool live = has_rows && minx < maxx;
+            const float dx0 = sub(x3, x2), dy0 = sub(y3, y2);
+            const bool cand = live && regular && !back;
+            const uint32_t rows = maxy - miny, span = maxx - minx;
+            // tight width <= 2  <=>  span <= 2 or floor(max_x) <= minx + 1   (see tight_width)
+            const bool foot = cand && rows <= 2u && (span <= 2u || __float2uint_rz(floorf(mx0)) <= minx + 1u);   // tier 1
+            bool beyond = cand && !foot;   // tier 2 / 3: handled in the rare block
 
-        // ---- tier 1: 2 x 3 footprint in registers, lockstep (same evaluation as k_geom3) ------------
-        uint32_t mask = 0;
-        if (__any_sync(0xFFFFFFFFu, foot)) {
-            float cr[2][3], gc[3][3];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const float py = (float)(miny + r);
-                cr[r][0] = mul(dx0, sub(py, y2));
-                cr[r][1] = mul(dx1, sub(py, y3));
-                cr[r][2] = mul(dx2, sub(py, y1));
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float px = (float)(minx + k);
-                gc[k][0] = mul(dy0, sub(px, x2));
-                gc[k][1] = mul(dy1, sub(px, x3));
-                gc[k][2] = mul(dy2, sub(px, x1));
-            }
-            uint32_t cov = 0;
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    // regular triangle: no NaN, so "all >= 0" == "none < 0"
-                    const float w0 = sub(cr[r][0], gc[k][0]), w1 = sub(cr[r][1], gc[k][1]), w2 = sub(cr[r][2], gc[k][2]);
-                    if (!(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f)) cov |= 1u << (r * 3 + k);
-                }
-            const uint32_t cm = (1u << min(span, 3u)) - 1u;
-            const uint32_t valid = cm | (rows > 1u ? cm << 3 : 0u);
-            // a row is finished after column 2 if a closing edge (dy >= 0) fails there
-            bool open = false;
-            if (span > 3u) {
-                const bool nd0 = !(dy0 < 0.0f), nd1 = !(dy1 < 0.0f), nd2 = !(dy2 < 0.0f);
+            // ---- tier 1: 2 x 3 footprint in registers, lockstep (same evaluation as k_geom3) ------------
+            if (__any_sync(0xFFFFFFFFu, foot)) {
+                float cr[2][3], gc[3][3];
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
-                    const bool closed = (nd0 && sub(cr[r][0], gc[2][0]) < 0.0f) || (nd1 && sub(cr[r][1], gc[2][1]) < 0.0f) ||
-                                        (nd2 && sub(cr[r][2], gc[2][2]) < 0.0f);
-                    if ((uint32_t)r < rows && !closed) open = true;
+                    const float py = (float)(miny + r);
+                    cr[r][0] = mul(dx0, sub(py, y2));
+                    cr[r][1] = mul(dx1, sub(py, y3));
+                    cr[r][2] = mul(dx2, sub(py, y1));
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float px = (float)(minx + k);
+                    gc[k][0] = mul(dy0, sub(px, x2));
+                    gc[k][1] = mul(dy1, sub(px, x3));
+                    gc[k][2] = mul(dy2, sub(px, x1));
+                }
+                uint32_t cov = 0;
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        // regular triangle: no NaN, so "all >= 0" == "none < 0"
+                        const float w0 = sub(cr[r][0], gc[k][0]), w1 = sub(cr[r][1], gc[k][1]), w2 = sub(cr[r][2], gc[k][2]);
+                        if (!(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f)) cov |= 1u << (r * 3 + k);
+                    }
+                const uint32_t cm = (1u << min(span, 3u)) - 1u;
+                const uint32_t valid = cm | (rows > 1u ? cm << 3 : 0u);
+                // a row is finished after column 2 if a closing edge (dy >= 0) fails there
+                bool open = false;
+                if (span > 3u) {
+                    const bool nd0 = !(dy0 < 0.0f), nd1 = !(dy1 < 0.0f), nd2 = !(dy2 < 0.0f);
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const bool closed = (nd0 && sub(cr[r][0], gc[2][0]) < 0.0f) || (nd1 && sub(cr[r][1], gc[2][1]) < 0.0f) ||
+                                            (nd2 && sub(cr[r][2], gc[2][2]) < 0.0f);
+                        if ((uint32_t)r < rows && !closed) open = true;
+                    }
+                }
+                if (foot) {
+                    if (open) beyond = true;   // sliver: the rare block hands it to k_tail
+                    else mask = cov & valid;
                 }
             }
-            if (foot) {
-                if (open) beyond = true;   // sliver: the rare block hands it to k_tail
-                else mask = cov & valid;
+
+            // ---- everything uncommon under one vote: tier 2, tier 3 / irregular queues, tall stamps ----
+            if (__any_sync(0xFFFFFFFFu, beyond || tall || (CHECK_REGULAR && live && !regular))) {
+                if (tall)
+                    for (uint32_t y = sy0; y < sy1; ++y) stamp(y, c + 1u);
+                uint32_t tw;
+                {
+                    const uint32_t f = __float2uint_rz(floorf(mx0));
+                    const uint32_t te = f >= maxx ? maxx : f + 1u;
+                    tw = te > minx ? te - minx : 0u;
+                }
+                bool walk = beyond;
+                const bool mid = beyond && !foot && rows <= 8u && tw <= 6u;   // tier 2: up to 8 x 8, one lane each
+                unsigned long long m64 = 0ull;
+                if (mid) {
+                    Setup s;
+                    s.x1 = x1; s.y1 = y1; s.x2 = x2; s.y2 = y2; s.x3 = x3; s.y3 = y3;
+                    s.dx0 = dx0; s.dy0 = dy0; s.dx1 = dx1; s.dy1 = dy1; s.dx2 = dx2; s.dy2 = dy2;
+                    unsigned long long m = 0ull;
+                    bool open = false;
+                    for (uint32_t r = 0; r < rows && !open; ++r) {
+                        const RowC rc = row_setup(s, miny + r);
+                        bool closed = false;
+                        for (uint32_t k = 0; k < 8u && k < span; ++k) {
+                            float w0, w1, w2;
+                            edge_eval(s, rc, minx + k, w0, w1, w2);
+                            if (!(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f)) m |= 1ull << (r * 8u + k);
+                            else if (row_closed(s, w0, w1, w2)) { closed = true; break; }
+                        }
+                        open = !closed && span > 8u;   // candidates remain right of the window
+                    }
+                    if (!open) { m64 = m; walk = false; }
+                }
+                while (__any_sync(0xFFFFFFFFu, m64 != 0ull)) {   // tier-2 fragments, one per lane and turn
+                    const bool has = m64 != 0ull;
+                    const uint32_t bit = has ? (uint32_t)__ffsll((long long)m64) - 1u : 0u;
+                    m64 &= m64 - 1ull;
+                    const unsigned who = __ballot_sync(0xFFFFFFFFu, has);
+                    if (has) {
+                        const uint32_t slot = (q_head + q_count + __popc(who & ((1u << lane) - 1u))) & (T_RING - 1u);
+                        wq.tri[slot] = t;
+                        wq.xy[slot] = (minx + (bit & 7u)) | ((miny + (bit >> 3)) << 16);
+                    }
+                    q_count += __popc(who);
+                    if (p.count_frags) nfrag_count += __popc(who);
+                    if (q_count >= 32u) {
+                        __syncwarp();
+                        t_emit(p, sc, wq, q_head, 32u, lane, keys);
+                        __syncwarp();
+                        q_head = (q_head + 32u) & (T_RING - 1u);
+                        q_count -= 32u;
+                    }
+                }
+                // tier 3: row-band work items for k_tail, one warp-aggregated atomic
+                const uint32_t walk_items = walk ? (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw) : 0u;
+                const unsigned need = __ballot_sync(0xFFFFFFFFu, walk_items > 0);
+                if (need) {
+                    uint32_t wi = walk_items;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t nn = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                        if ((int)lane >= d) wi += nn;
+                    }
+                    const uint32_t total = __shfl_sync(0xFFFFFFFFu, wi, 31);
+                    unsigned long long old = 0;
+                    if (lane == 0)
+                        old = atomicAdd(&q.aux->walk_counter, ((unsigned long long)__popc(need) << ITEM_BITS) | total);
+                    old = __shfl_sync(0xFFFFFFFFu, old, 0);
+                    if (walk_items > 0) {
+                        const uint32_t slot = (uint32_t)(old >> ITEM_BITS) + __popc(need & ((1u << lane) - 1u));
+                        q.walk_tri[slot] = t;
+                        q.walk_base[slot] = (old & ITEM_MASK) + (wi - walk_items);
+                    }
+                }
+                if (CHECK_REGULAR) {
+                    const unsigned irr = __ballot_sync(0xFFFFFFFFu, live && !regular);
+                    if (irr) {
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&q.aux->irr_count, (uint32_t)__popc(irr));
+                        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                        if (live && !regular) q.irr_tri[base + __popc(irr & ((1u << lane) - 1u))] = t;
+                    }
+                }
             }
         }
 
-        // park one fragment per lane that has one; returns after emitting full groups of 32
-        auto park = [&](bool has, uint32_t x, uint32_t y) {
+        // ---- the coordinates of this chunk are dead: this set takes the chunk whose record is in rn (its
+        // gathers have a whole body of the other set to land), the record register moves one chunk on.
+        P1 = __ldg(sc.vxy + rn.x); P2 = __ldg(sc.vxy + rn.y); P3 = __ldg(sc.vxy + rn.z);
+        c_set = cN;
+        cN = next_live(cN);
+        rn = load_rec(cN);
+        // ... and the record lines a few chunks further on are pulled into L2: one 512-byte load per warp in
+        // flight cannot keep HBM busy (Little's law), the prefetches cost no registers
+        if (pf_dist) asm volatile("prefetch.global.L2 [%0];" ::"l"(sc.rec + min(cN + pf_dist, last) * 32u + lane));
+
+        // ---- phase C: park the covered fragments of the 2 x 3 footprint, one per lane and turn; every 32
+        // parked fragments are emitted with all lanes busy ---------------------------------------------
+        const uint32_t xy0 = minx | (miny << 16);
+        while (__any_sync(0xFFFFFFFFu, mask != 0u)) {
+            const bool has = mask != 0u;
+            const uint32_t bit = (uint32_t)__ffs((int)mask) - 1u;   // garbage when !has, unused
+            mask &= mask - 1u;
             const unsigned who = __ballot_sync(0xFFFFFFFFu, has);
             if (has) {
                 const uint32_t slot = (q_head + q_count + __popc(who & ((1u << lane) - 1u))) & (T_RING - 1u);
-                wq.i0[slot] = i0; wq.i1[slot] = i1; wq.i2[slot] = i2;
                 wq.tri[slot] = t;
-                wq.xy[slot] = x | (y << 16);
+                wq.xy[slot] = xy0 + bit + (bit >= 3u ? 65536u - 3u : 0u);   // bit = row * 3 + column
             }
-            const uint32_t n = __popc(who);
-            q_count += n;
-            nfrag_count += n;
+            q_count += __popc(who);
+            if (p.count_frags) nfrag_count += __popc(who);
             if (q_count >= 32u) {
                 __syncwarp();
                 t_emit(p, sc, wq, q_head, 32u, lane, keys);
@@ -228,99 +343,32 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
                 q_head = (q_head + 32u) & (T_RING - 1u);
                 q_count -= 32u;
             }
-        };
-
-        // ---- everything uncommon under one vote: tier 2, tier 3 / irregular queues, tall stamps ----
-        if (__any_sync(0xFFFFFFFFu, beyond || tall || (CHECK_REGULAR && live && !regular))) {
-            if (tall)
-                for (uint32_t y = sy0; y < sy1; ++y) atomicMax(rowmax + y, c + 1u);
-            uint32_t tw;
-            {
-                const uint32_t f = __float2uint_rz(floorf(mx0));
-                const uint32_t te = f >= maxx ? maxx : f + 1u;
-                tw = te > minx ? te - minx : 0u;
-            }
-            bool walk = beyond;
-            const bool mid = beyond && !foot && rows <= 8u && tw <= 6u;   // tier 2: up to 8 x 8, one lane each
-            unsigned long long m64 = 0ull;
-            if (mid) {
-                Setup s;
-                s.x1 = x1; s.y1 = y1; s.x2 = x2; s.y2 = y2; s.x3 = x3; s.y3 = y3;
-                s.dx0 = dx0; s.dy0 = dy0; s.dx1 = dx1; s.dy1 = dy1; s.dx2 = dx2; s.dy2 = dy2;
-                unsigned long long m = 0ull;
-                bool open = false;
-                for (uint32_t r = 0; r < rows && !open; ++r) {
-                    const RowC rc = row_setup(s, miny + r);
-                    bool closed = false;
-                    for (uint32_t k = 0; k < 8u && k < span; ++k) {
-                        float w0, w1, w2;
-                        edge_eval(s, rc, minx + k, w0, w1, w2);
-                        if (!(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f)) m |= 1ull << (r * 8u + k);
-                        else if (row_closed(s, w0, w1, w2)) { closed = true; break; }
-                    }
-                    open = !closed && span > 8u;   // candidates remain right of the window
-                }
-                if (!open) { m64 = m; walk = false; }
-            }
-            while (__any_sync(0xFFFFFFFFu, m64 != 0ull)) {   // tier-2 fragments, one per lane and turn
-                const bool has = m64 != 0ull;
-                const uint32_t bit = has ? (uint32_t)__ffsll((long long)m64) - 1u : 0u;
-                m64 &= m64 - 1ull;
-                park(has, minx + (bit & 7u), miny + (bit >> 3));
-            }
-            // tier 3: row-band work items for k_tail, one warp-aggregated atomic
-            const uint32_t walk_items = walk ? (rows + walk_rows_per_item(tw) - 1u) / walk_rows_per_item(tw) : 0u;
-            const unsigned need = __ballot_sync(0xFFFFFFFFu, walk_items > 0);
-            if (need) {
-                uint32_t wi = walk_items;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t nn = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-                    if ((int)lane >= d) wi += nn;
-                }
-                const uint32_t total = __shfl_sync(0xFFFFFFFFu, wi, 31);
-                unsigned long long old = 0;
-                if (lane == 0)
-                    old = atomicAdd(&q.aux->walk_counter, ((unsigned long long)__popc(need) << ITEM_BITS) | total);
-                old = __shfl_sync(0xFFFFFFFFu, old, 0);
-                if (walk_items > 0) {
-                    const uint32_t slot = (uint32_t)(old >> ITEM_BITS) + __popc(need & ((1u << lane) - 1u));
-                    q.walk_tri[slot] = t;
-                    q.walk_base[slot] = (old & ITEM_MASK) + (wi - walk_items);
-                }
-            }
-            if (CHECK_REGULAR) {
-                const unsigned irr = __ballot_sync(0xFFFFFFFFu, live && !regular);
-                if (irr) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&q.aux->irr_count, (uint32_t)__popc(irr));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (live && !regular) q.irr_tri[base + __popc(irr & ((1u << lane) - 1u))] = t;
-                }
-            }
         }
 
-        // ---- phase C: park the covered fragments of the 2 x 3 footprint, one per lane and turn ------
-        while (__any_sync(0xFFFFFFFFu, mask != 0u)) {
-            const bool has = mask != 0u;
-            const uint32_t bit = has ? (uint32_t)__ffs((int)mask) - 1u : 0u;
-            mask &= mask - 1u;
-            const uint32_t r = bit >= 3u ? 1u : 0u;
-            park(has, minx + bit - 3u * r, miny + r);
-        }
-
-        c = c1;
-        c1 = c2;
+    };
+    for (;;) {
+        if (cA >= n_chunks) break;
+        body(A1, A2, A3, cA);
+        if (cB >= n_chunks) break;
+        body(B1, B2, B3, cB);
     }
     if (q_count) {
         __syncwarp();
         t_emit(p, sc, wq, q_head, q_count, lane, keys);
     }
-    if (do_stamps && rowmax_shared) {   // publish this block's stamps (the probe skips most atomics)
+    if (ROWMAX_SHARED && do_stamps) {   // publish this block's stamps (the probe skips most atomics)
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n_rowmax - 64u; i += blockDim.x) {
-            const uint32_t m = s_rowmax[i];
-            if (m && __ldcg(q.rowmax + i) < m) atomicMax(q.rowmax + i, m);
+        for (uint32_t i0 = threadIdx.x; i0 < n_rowmax - 64u; i0 += 4u * blockDim.x) {
+            uint32_t m[4], g[4];   // four probes in flight per thread: the loop is latency, not bandwidth
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k) {
+                const uint32_t i = i0 + k * blockDim.x;
+                m[k] = i < n_rowmax - 64u ? s_rowmax[i] : 0u;
+                g[k] = m[k] ? __ldcg(q.rowmax + i) : 0xFFFFFFFFu;
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k)
+                if (g[k] < m[k]) atomicMax(q.rowmax + i0 + k * blockDim.x, m[k]);
         }
     }
     if (p.count_frags && lane == 0) {

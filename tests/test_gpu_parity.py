@@ -492,10 +492,10 @@ def test_indexed_scene_dedupes_by_bit_pattern_and_auto_picks_the_path():
         assert_same(cells, z, ocells, oz, "icosphere, AUTO -> indexed")
         # the caller's own indexing: unique rows of the soup + inverse map
         corners = np.ascontiguousarray(xyz.reshape(-1, 3))
-        keys = corners.view(np.uint32).astype(np.uint64)
-        packed = (keys[:, 0] << np.uint64(40)) ^ (keys[:, 1] << np.uint64(20)) ^ keys[:, 2]
-        _, first, inv = np.unique(packed, return_index=True, return_inverse=True)
-        assert np.array_equal(corners[first][inv].view(np.uint32), corners.view(np.uint32)), "test hash collided"
+        rows = corners.view(np.uint32).view([("x", np.uint32), ("y", np.uint32), ("z", np.uint32)]).reshape(-1)
+        _, first, inv = np.unique(rows, return_index=True, return_inverse=True)
+        inv = inv.reshape(-1)
+        assert np.array_equal(corners[first][inv].view(np.uint32), corners.view(np.uint32))
         ctx.set_scene_indexed(corners[first], inv.reshape(-1, 3), rgb, s0)
         assert ctx.stats()["n_vert"] == 10 * f * f + 2
         cells2, z2 = ctx.render(rot, want_z=True)
