@@ -17,6 +17,7 @@
 #include <cstring>
 #include <limits>
 #include <new>
+#include <vector>
 
 #include "../../include/sloth_b200.h"
 #include "kernels.cuh"
@@ -102,12 +103,16 @@ struct sloth_ctx {
     float* sc_pos = nullptr;          // x[n_vert+1] y[n_vert+1] z[n_vert+1] (one allocation, SoA)
     size_t pos_stride = 0;            // floats between the x, y and z arrays
     uint4* sc_rec = nullptr;          // [n_tri padded to 32]
-    float2* vxy = nullptr;            // [n_vert + 1], rewritten every frame
-    float* vz = nullptr;
+    float2* vxy[2] = {nullptr, nullptr};   // [n_vert + 1] per frame-state set, rewritten every frame (one allocation)
+    float* vz[2] = {nullptr, nullptr};
+    cudaStream_t xform_stream = nullptr;   // batches: k_xform of frame k+1 runs beside k_tri of frame k
+    cudaEvent_t ev_xform[2] = {nullptr, nullptr};
+    cudaEvent_t ev_batch_start = nullptr;
     uint32_t tri_blocks_per_sm = T_BLOCKS_PER_SM;   // SLOTH_TGRID overrides (profiling)
     uint32_t pf_chunks = 0;           // SLOTH_PF: L2 prefetch distance of k_tri's record stream (measured: hurts, off)
     size_t l2_persist_max = 0, l2_window_max = 0;   // device limits of the persisting-L2 set-aside / access window
     size_t l2_window_bytes = 0;       // bytes of (vxy, vz) currently covered by the persisting window
+    bool l2_persist = false;          // SLOTH_L2PERSIST=1: measured neutral for k_tri and 4 us slower for k_resolve, so off
 
     // frame state
     uint32_t W = 0, H = 0;
@@ -275,10 +280,21 @@ Queues make_queues(const sloth_ctx* c, int set)
     return q;
 }
 
-Scene scene_of(const sloth_ctx* c)
+Scene scene_of(const sloth_ctx* c, int set)
 {
-    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb, c->sc_bounds, c->sc_rec, c->vxy, c->vz};
+    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb, c->sc_bounds, c->sc_rec, c->vxy[set], c->vz[set]};
     return sc;
+}
+
+// Triangle::mul once per unique vertex of the indexed scene, into frame-state set `set`, on stream `st`.
+int enqueue_xform(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
+{
+    const float* px = c->sc_pos;
+    const uint32_t n_threads = (c->n_vert + 1 + XFORM_PER_THREAD - 1) / XFORM_PER_THREAD;
+    k_xform<<<(n_threads + 255) / 256, 256, 0, st>>>(p, px, px + c->pos_stride, px + 2 * c->pos_stride, c->n_vert, c->vxy[set],
+                                                     c->vz[set]);
+    c->launches += 1;
+    return SLOTH_OK;
 }
 
 // Kernels that run side by side on one SM (the geometry kernel of frame k+1 with k_tail / k_resolve of frame k)
@@ -314,9 +330,10 @@ int apply_carveout(sloth_ctx* c, int pct)
     return SLOTH_OK;
 }
 
-// Indexed path: k_xform (Triangle::mul once per unique vertex) then k_tri, both on stream `st`.
+// Indexed path: k_xform (Triangle::mul once per unique vertex; skipped when the caller has already run it for this
+// set on another stream) then k_tri, on stream `st`.
 int enqueue_geometry_indexed(sloth_ctx* c, const FrameParams& p, const Scene& sc, const Queues& q, int set, cudaStream_t st,
-                             bool kt)
+                             bool kt, bool xform_done)
 {
     const uint32_t n_chunks = (c->n_tri + 31) / 32;
     const uint32_t bps = c->tri_blocks_per_sm;
@@ -325,7 +342,7 @@ int enqueue_geometry_indexed(sloth_ctx* c, const FrameParams& p, const Scene& sc
     bool bounded = c->scene_clean;
     for (int i = 0; i < 8; ++i) bounded = bounded && std::fabs(p.m[i]) <= 131072.0f;
     const bool rowmax_shared = c->rowmax_bytes <= 33024u;
-    const size_t dyn = rowmax_shared ? c->rowmax_bytes : 0;
+    const size_t dyn = (rowmax_shared ? c->rowmax_bytes : 0) + sizeof(TWarpSmem) * T_WARPS;
     const bool band_mode = c->row1 != 0;
     void (*kern)(FrameParams, Scene, unsigned long long*, Queues);
     if (rowmax_shared)
@@ -335,28 +352,27 @@ int enqueue_geometry_indexed(sloth_ctx* c, const FrameParams& p, const Scene& sc
         kern = bounded ? (band_mode ? k_tri<false, true, false> : k_tri<false, false, false>)
                        : (band_mode ? k_tri<true, true, false> : k_tri<true, false, false>);
     {
-        const size_t per_block = sizeof(TRing) * T_WARPS + dyn + 1024;
+        const size_t per_block = dyn + 1024;
         int pct = (int)((per_block * bps * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
         pct = std::min(100, std::max(25, pct));
         const int rc = apply_carveout(c, pct);
         if (rc) return rc;
     }
-    const float* px = c->sc_pos;
-    k_xform<<<(c->n_vert + 1 + 255) / 256, 256, 0, st>>>(p, px, px + c->pos_stride, px + 2 * c->pos_stride, c->n_vert, c->vxy, c->vz);
+    if (!xform_done) enqueue_xform(c, p, set, st);
     if (kt) CU(cudaEventRecord(c->ev[EV_XFORM], st));
     kern<<<grid, T_WARPS * 32, dyn, st>>>(p, sc, c->keys[set], q);
-    c->launches += 2;
+    c->launches += 1;
     if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
     return SLOTH_OK;
 }
 
 // Geometry pass of a frame (aux clear, k_geom3) on stream `st`, into frame-state set `set`.
-int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st, bool kt)
+int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st, bool kt, bool xform_done = false)
 {
-    const Scene sc = scene_of(c);
+    const Scene sc = scene_of(c, set);
     const Queues q = make_queues(c, set);
     CU(cudaMemsetAsync(c->aux_region[set], 0, c->aux_bytes, st));
-    if (c->indexed && c->n_tri) return enqueue_geometry_indexed(c, p, sc, q, set, st, kt);
+    if (c->indexed && c->n_tri) return enqueue_geometry_indexed(c, p, sc, q, set, st, kt, xform_done);
     if (c->n_tri) {
         {
             const uint32_t n_chunks = (c->n_tri + 31) / 32;
@@ -403,7 +419,7 @@ int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t s
 int enqueue_tail(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
 {
     if (!c->n_tri) return SLOTH_OK;
-    const Scene sc = scene_of(c);
+    const Scene sc = scene_of(c, set);
     const Queues q = make_queues(c, set);
     const uint32_t wb = (uint32_t)c->sm_count * c->tail_blocks_per_sm, ib = std::max<uint32_t>(1u, (uint32_t)c->sm_count / 2u);
     k_tail<<<wb + ib, 128, 0, st>>>(p, sc, c->keys[set], q, wb);
@@ -414,7 +430,7 @@ int enqueue_tail(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
 // Resolve half of a frame (optional z plane, key plane -> cells, key plane reset) on stream `st`.
 int enqueue_resolve(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st, uint32_t* d_out, float* d_z)
 {
-    const Scene sc = scene_of(c);
+    const Scene sc = scene_of(c, set);
     const Queues q = make_queues(c, set);
     const bool band = c->row1 != 0;
     const uint32_t rows = p.row1 - p.row0;
@@ -427,8 +443,10 @@ int enqueue_resolve(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st
     }
     if ((c->W & 1u) == 0) {
         const uint32_t n_slots = rows * p.KW;
-        const uint32_t n = n_slots + n_tail;
-        if (n) k_resolve_even<<<(n + 255) / 256, 256, 0, st>>>(p, sc, c->keys[set], q, d_out, n_slots, n_tail);
+        // a warp owns 32 * RESOLVE_SLOTS consecutive slots
+        const uint32_t per_warp = 32u * RESOLVE_SLOTS;
+        const uint32_t n_threads = std::max<uint32_t>((n_slots + per_warp - 1) / per_warp * 32u, n_tail ? 32u : 0u);
+        if (n_threads) k_resolve_even<<<(n_threads + 255) / 256, 256, 0, st>>>(p, sc, c->keys[set], q, d_out, n_slots, n_tail);
         c->launches += 1;
     } else {
         const uint32_t n_cells = rows * c->W;
@@ -472,21 +490,43 @@ template <typename BeforeFn, typename OutFn, typename AfterFn>
 int enqueue_overlapped(sloth_ctx* c, const float* rots, size_t n_frames, BeforeFn before_resolve, OutFn out,
                        AfterFn after_resolve)
 {
+    CU(cudaEventRecord(c->ev_batch_start, c->stream));   // work enqueued on the context stream before this batch comes first
+    // SLOTH_DEBUG bit 9: timeline of the first frames of the batch (timing events on all three streams), printed to stderr
+    const bool trace = (c->debug & 512u) && n_frames >= 4;
+    const size_t n_trace = trace ? std::min<size_t>(n_frames, 12) : 0;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+    mark(c->stream);
     for (size_t k = 0; k < n_frames; ++k) {
+        const bool tr = k < n_trace;
         const int set = (int)(k & 1);
         FrameParams p;
         build_params(c, rots + 16 * k, p);
+        const bool split = c->indexed && c->n_tri;
+        if (split) {   // k_xform(k) on its own stream: it runs beside k_tri(k-1), as soon as k_tri(k-2) has let go of the set
+            if (k >= 2) CU(cudaStreamWaitEvent(c->xform_stream, c->ev_geom_done[set], 0));
+            else CU(cudaStreamWaitEvent(c->xform_stream, c->ev_batch_start, 0));
+            if (tr) mark(c->xform_stream);
+            if (!(c->debug & 64u) || k < 2) enqueue_xform(c, p, set, c->xform_stream);   // bit 6: timing experiment (wrong frames)
+            if (tr) mark(c->xform_stream);
+            CU(cudaEventRecord(c->ev_xform[set], c->xform_stream));
+            CU(cudaStreamWaitEvent(c->stream, c->ev_xform[set], 0));
+        }
         if (k >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_resolved[set], 0));   // set's key plane and aux are free again
-        int rc = enqueue_geometry(c, p, set, c->stream, false);
+        if (tr) mark(c->stream);
+        int rc = enqueue_geometry(c, p, set, c->stream, false, split);
         if (rc) return rc;
+        if (tr) mark(c->stream);
         CU(cudaEventRecord(c->ev_geom_done[set], c->stream));
         CU(cudaStreamWaitEvent(c->resolve_stream, c->ev_geom_done[set], 0));
-        rc = enqueue_tail(c, p, set, c->resolve_stream);   // k_tail(k) and resolve(k) run beside k_geom3(k+1)
+        if (tr) mark(c->resolve_stream);
+        if (!(c->debug & 128u)) rc = enqueue_tail(c, p, set, c->resolve_stream);   // k_tail(k) and resolve(k) run beside k_geom3(k+1)
         if (rc) return rc;
         rc = before_resolve(k);
         if (rc) return rc;
-        rc = enqueue_resolve(c, p, set, c->resolve_stream, out(k), nullptr);
+        if (!(c->debug & 256u)) rc = enqueue_resolve(c, p, set, c->resolve_stream, out(k), nullptr);   // bits 7, 8: timing experiments
         if (rc) return rc;
+        if (tr) mark(c->resolve_stream);
         CU(cudaEventRecord(c->ev_resolved[set], c->resolve_stream));
         rc = after_resolve(k);
         if (rc) return rc;
@@ -495,6 +535,22 @@ int enqueue_overlapped(sloth_ctx* c, const float* rots, size_t n_frames, BeforeF
     }
     for (int set = 0; set < 2 && (size_t)set < n_frames; ++set) CU(cudaStreamWaitEvent(c->stream, c->ev_resolved[set], 0));
     CU(cudaGetLastError());
+    if (trace) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaStreamSynchronize(c->resolve_stream));
+        const size_t per = (c->indexed && c->n_tri) ? 6 : 4;
+        std::fprintf(stderr, "[sloth trace] us since batch start: frame  xform[begin end]  geometry[begin end]  tail+resolve[begin end]\n");
+        for (size_t k = 0; k < n_trace; ++k) {
+            std::fprintf(stderr, "[sloth trace] %2zu", k);
+            for (size_t j = 0; j < per; ++j) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, tev[0], tev[1 + k * per + j]);
+                std::fprintf(stderr, " %8.1f", ms * 1e3f);
+            }
+            std::fprintf(stderr, "\n");
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     return SLOTH_OK;
 }
 
@@ -551,8 +607,9 @@ int check_ready(sloth_ctx* c)
 
 void free_index(sloth_ctx* c)
 {
-    cudaFree(c->sc_pos); cudaFree(c->sc_rec); cudaFree(c->vxy);   // vz lives in vxy's allocation
-    c->sc_pos = nullptr; c->sc_rec = nullptr; c->vxy = nullptr; c->vz = nullptr;
+    cudaFree(c->sc_pos); cudaFree(c->sc_rec); cudaFree(c->vxy[0]);   // both sets of (vxy, vz) live in one allocation
+    c->sc_pos = nullptr; c->sc_rec = nullptr;
+    c->vxy[0] = c->vxy[1] = nullptr; c->vz[0] = c->vz[1] = nullptr;
     if (c->l2_window_bytes) {   // drop the residency window of the transformed vertices
         cudaStreamAttrValue attr;
         std::memset(&attr, 0, sizeof attr);
@@ -574,23 +631,26 @@ int alloc_index(sloth_ctx* c, size_t n_vert, size_t n_tri)
     CU(cudaMalloc(&c->sc_pos, 3 * c->pos_stride * sizeof(float)));
     CU(cudaMalloc(&c->sc_rec, std::max<size_t>(n_padded, 32) * sizeof(uint4)));
     // (x', y') and z' of every vertex in one allocation, so that one L2 access-policy window covers both
-    const size_t xy_bytes = ((n_vert + 1) * sizeof(float2) + 255) & ~(size_t)255;
-    const size_t all_bytes = xy_bytes + (n_vert + 1) * sizeof(float);
-    CU(cudaMalloc(&c->vxy, all_bytes));
-    c->vz = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(c->vxy) + xy_bytes);
+    const size_t n_slots = (n_vert + 1 + XFORM_PER_THREAD - 1) / XFORM_PER_THREAD * XFORM_PER_THREAD;   // k_xform writes whole groups
+    const size_t xy_bytes = (n_slots * sizeof(float2) + 255) & ~(size_t)255;
+    const size_t all_bytes = xy_bytes + n_slots * sizeof(float);
+    const size_t set_bytes = (all_bytes + 255) & ~(size_t)255;
+    CU(cudaMalloc(&c->vxy[0], 2 * set_bytes));
+    c->vxy[1] = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(c->vxy[0]) + set_bytes);
+    for (int i = 0; i < 2; ++i) c->vz[i] = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(c->vxy[i]) + xy_bytes);
     c->n_vert = (uint32_t)n_vert;
     // Keep the transformed vertices resident in L2 between k_xform (writes them) and k_tri (gathers them): the
     // triangle records stream past them at 16 B/triangle and would otherwise push half of them out to HBM
     // (ncu: 50 % of the gather sectors missed L2).  Persisting lines live in a set-aside part of L2; when the
     // set-aside is smaller than the window, hitRatio keeps only that fraction persisting (no thrash).
     c->l2_window_bytes = 0;
-    if (c->l2_persist_max && c->l2_window_max && all_bytes >= (1u << 20) && !(c->debug & 32u)) {
+    if (c->l2_persist && c->l2_persist_max && c->l2_window_max && all_bytes >= (1u << 20)) {
         const size_t window = std::min(all_bytes, c->l2_window_max);
         const size_t carve = std::min(window, c->l2_persist_max);
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
             cudaStreamAttrValue attr;
             std::memset(&attr, 0, sizeof attr);
-            attr.accessPolicyWindow.base_ptr = c->vxy;
+            attr.accessPolicyWindow.base_ptr = c->vxy[0];
             attr.accessPolicyWindow.num_bytes = window;
             attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
             attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -610,7 +670,7 @@ int build_index(sloth_ctx* c, size_t n_tri)
 {
     free_index(c);
     if (!n_tri || c->path_pref == SLOTH_PATH_SOUP) return SLOTH_OK;
-    const Scene sc = scene_of(c);
+    const Scene sc = scene_of(c, 0);
     const size_t n_corners = 3 * n_tri;
     size_t cap = 64;
     while (cap < 2 * n_corners) cap <<= 1;
@@ -752,16 +812,34 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     if (const char* g = std::getenv("SLOTH_BATCH")) c->batch_max = (uint32_t)std::min(16, std::max(1, std::atoi(g)));
     if (const char* g = std::getenv("SLOTH_GRID")) c->geom_blocks_per_sm = (uint32_t)std::max(1, std::atoi(g));
     if (const char* g = std::getenv("SLOTH_TGRID")) c->tri_blocks_per_sm = (uint32_t)std::min((int)T_BLOCKS_PER_SM, std::max(1, std::atoi(g)));
+    if (const char* g = std::getenv("SLOTH_L2PERSIST")) c->l2_persist = std::atoi(g) != 0;
     if (const char* g = std::getenv("SLOTH_PF")) c->pf_chunks = (uint32_t)std::min(64, std::max(0, std::atoi(g)));
     if (const char* g = std::getenv("SLOTH_PATH")) c->path_pref = std::min(2, std::max(0, std::atoi(g)));
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        // The geometry kernel of frame k+1 must reach the SMs the moment frame k's ends: it is the critical path of a
+        // batch, the other streams' kernels (k_tail / resolve of frame k, k_xform of frame k+2) fill in beside its
+        // persistent blocks.  Measured on the 10 M-triangle frame: geometry highest / others lowest 142 us per frame,
+        // all lowest 154 us, resolve highest (round 1's choice for the soup kernel) 168 us.
+        const char* pr = std::getenv("SLOTH_GEOM_PRIO");   // profiling knob: 0 = lowest priority instead
+        CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, (pr && std::atoi(pr) == 0) ? lo : hi));
+    }
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     {
-        int lo = 0, hi = 0;   // resolve kernels squeeze in beside the persistent geometry blocks: give them priority
+        int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        const char* pr = std::getenv("SLOTH_RESOLVE_PRIO");   // profiling knob: 0 = lowest priority instead of highest
-        CU(cudaStreamCreateWithPriority(&c->resolve_stream, cudaStreamNonBlocking, (pr && std::atoi(pr) == 0) ? lo : hi));
+        const char* pr = std::getenv("SLOTH_RESOLVE_PRIO");   // profiling knob: 1 = highest priority instead of lowest
+        CU(cudaStreamCreateWithPriority(&c->resolve_stream, cudaStreamNonBlocking, (pr && std::atoi(pr) == 1) ? hi : lo));
     }
+    {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const char* pr = std::getenv("SLOTH_XFORM_PRIO");   // profiling knob: 1 = highest priority for the k_xform stream
+        CU(cudaStreamCreateWithPriority(&c->xform_stream, cudaStreamNonBlocking, (pr && std::atoi(pr) == 1) ? hi : lo));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_batch_start, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&c->ev_xform[i], cudaEventDisableTiming));
     for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) {
         CU(cudaEventCreateWithFlags(&c->ev_rendered[i], cudaEventDisableTiming));
@@ -784,6 +862,15 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
         CU(cudaFuncSetAttribute(k_geom3<false, true, true>, a, lim));
         CU(cudaFuncSetAttribute(k_geom3<true, false, true>, a, lim));
         CU(cudaFuncSetAttribute(k_geom3<true, true, true>, a, lim));
+        const int tlim = 96 * 1024;   // k_tri: cp.async rings + fragment rings (45 KB) + up to 33 KB of row stamps
+        CU(cudaFuncSetAttribute(k_tri<false, false, true>, a, tlim));
+        CU(cudaFuncSetAttribute(k_tri<false, true, true>, a, tlim));
+        CU(cudaFuncSetAttribute(k_tri<true, false, true>, a, tlim));
+        CU(cudaFuncSetAttribute(k_tri<true, true, true>, a, tlim));
+        CU(cudaFuncSetAttribute(k_tri<false, false, false>, a, tlim));
+        CU(cudaFuncSetAttribute(k_tri<false, true, false>, a, tlim));
+        CU(cudaFuncSetAttribute(k_tri<true, false, false>, a, tlim));
+        CU(cudaFuncSetAttribute(k_tri<true, true, false>, a, tlim));
     }
     *out = c;
     return SLOTH_OK;
@@ -822,6 +909,9 @@ int sloth_ctx_destroy(sloth_ctx* c)
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->resolve_stream);
+    if (c->xform_stream) cudaStreamDestroy(c->xform_stream);
+    if (c->ev_batch_start) cudaEventDestroy(c->ev_batch_start);
+    for (int i = 0; i < 2; ++i) if (c->ev_xform[i]) cudaEventDestroy(c->ev_xform[i]);
     delete c;
     return SLOTH_OK;
 }

@@ -231,24 +231,36 @@ __global__ void __launch_bounds__(256) k_ix_expand_input(const float* __restrict
 
 // ---------------------------------------------------------------------------------
 // k_xform: Triangle::mul (geometry.rs:43-48) once per unique vertex, gemv/axcpy order (xform_row), so every
-// x', y', z' is bit-identical to what the soup path computes per corner.  One thread per vertex, coalesced SoA
-// loads, (x', y') as one 8-byte store (what k_tri gathers), z' beside it (gathered for covering triangles only).
-// Slot n_vert is the sentinel the padding records point at: far off-screen, no rows, no candidates.
+// x', y', z' is bit-identical to what the soup path computes per corner.  Four consecutive vertices per thread:
+// three 16-byte SoA loads, (x', y') as two 16-byte stores (what k_tri gathers), z' as one (gathered for covering
+// triangles only) -- few instructions and enough bytes in flight per thread to run beside the previous frame's
+// k_tri at one block per SM.  Slot n_vert is the sentinel the padding records point at: far off-screen, no rows,
+// no candidates.  The position arrays and the outputs are padded to whole groups of four.
 // ---------------------------------------------------------------------------------
+static constexpr uint32_t XFORM_PER_THREAD = 4;
+
 __global__ void __launch_bounds__(256) k_xform(const __grid_constant__ FrameParams p, const float* __restrict__ px,
                                                const float* __restrict__ py, const float* __restrict__ pz, uint32_t n_vert,
                                                float2* __restrict__ vxy, float* __restrict__ vz)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * XFORM_PER_THREAD;
     if (i > n_vert) return;
-    if (i == n_vert) {
-        vxy[i] = make_float2(-1.0e30f, -1.0e30f);
-        vz[i] = 0.0f;
-        return;
+    const float4 X = __ldcs(reinterpret_cast<const float4*>(px + i));
+    const float4 Y = __ldcs(reinterpret_cast<const float4*>(py + i));
+    const float4 Z = __ldcs(reinterpret_cast<const float4*>(pz + i));
+    const float x[4] = {X.x, X.y, X.z, X.w}, y[4] = {Y.x, Y.y, Y.z, Y.w}, z[4] = {Z.x, Z.y, Z.z, Z.w};
+    float ox[4], oy[4], oz[4];
+#pragma unroll
+    for (uint32_t k = 0; k < 4u; ++k) {
+        ox[k] = xform_row(p.m + 0, x[k], y[k], z[k]);
+        oy[k] = xform_row(p.m + 4, x[k], y[k], z[k]);
+        oz[k] = xform_row(p.m + 8, x[k], y[k], z[k]);
+        if (i + k >= n_vert) { ox[k] = oy[k] = -1.0e30f; oz[k] = 0.0f; }   // the sentinel (and the padding after it)
     }
-    const float x = __ldcs(px + i), y = __ldcs(py + i), z = __ldcs(pz + i);
-    vxy[i] = make_float2(xform_row(p.m + 0, x, y, z), xform_row(p.m + 4, x, y, z));
-    vz[i] = xform_row(p.m + 8, x, y, z);
+    float4* oxy = reinterpret_cast<float4*>(vxy + i);
+    oxy[0] = make_float4(ox[0], oy[0], ox[1], oy[1]);
+    oxy[1] = make_float4(ox[2], oy[2], ox[3], oy[3]);
+    *reinterpret_cast<float4*>(vz + i) = make_float4(oz[0], oz[1], oz[2], oz[3]);
 }
 
 }  // namespace sloth

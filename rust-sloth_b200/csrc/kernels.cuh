@@ -640,36 +640,74 @@ SLOTH_DEV bool stamp_beats_fragment(const FrameParams& p, const Scene& sc, const
     return newline;
 }
 
-// W even: ids are even, one key slot owns cells (2k, 2k+1) of its row.  One slot per thread
-// (two slots per thread with 16-byte accesses measured 3x slower: half the warps, same
-// dependent load -> gather chain, so less latency hiding).
+// W even: ids are even, one key slot owns cells (2k, 2k+1) of its row.  Four slots per thread, 32 apart (every
+// access of a warp is one contiguous 256-byte run): the key -> colour gather is a dependent load chain, so each
+// thread keeps four of them in flight -- the kernel usually runs as one block per SM beside the next frame's
+// geometry kernel, where only instruction-level parallelism hides the latency.  Row / column of a slot cost one
+// division per thread instead of one per slot; the newline-order check (warp-cooperative) is only entered when
+// some lane of the warp has a contested cell.
+static constexpr uint32_t RESOLVE_SLOTS = 4;   // per thread
+
 __global__ void __launch_bounds__(256) k_resolve_even(const __grid_constant__ FrameParams p, const Scene sc,
                                                       unsigned long long* __restrict__ keys, const Queues q,
                                                       uint32_t* __restrict__ cells, uint32_t n_slots,
                                                       uint32_t n_tail)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i0 = (tid >> 5) * (32u * RESOLVE_SLOTS) + (tid & 31u);   // this thread's slots: i0 + 32 m
     const uint32_t blank = (uint32_t)' ';
-    unsigned long long key = KEY_EMPTY;
-    uint32_t c0 = blank, c1 = blank, row = 0;
-    bool stamped = false;
-    if (i < n_slots) {
-        key = keys[i];
-        keys[i] = KEY_EMPTY;  // the key plane is clean again for the next frame
-        if (key != KEY_EMPTY) c0 = c1 = cell_of(p, sc, key);
-        row = p.row0 + i / p.KW;
-        stamped = p.image && i % p.KW == 0u && q.rowmax[row] != 0u;   // this slot owns cells (row,0),(row,1)
+    unsigned long long key[RESOLVE_SLOTS];
+#pragma unroll
+    for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m) {
+        const uint32_t i = i0 + 32u * m;
+        key[m] = KEY_EMPTY;
+        if (i < n_slots) {
+            key[m] = keys[i];
+            keys[i] = KEY_EMPTY;   // the key plane is clean again for the next frame
+        }
     }
-    if (p.image) {   // warp-uniform; the order check is warp-cooperative
-        const bool contested = stamped && key != KEY_EMPTY;
-        const bool nl = stamp_beats_fragment(p, sc, q, contested, row, key_tri(key));
-        if (stamped && (!contested || nl)) c1 = (uint32_t)'\n';
+    uint32_t c0[RESOLVE_SLOTS], c1[RESOLVE_SLOTS];
+#pragma unroll
+    for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m) {
+        c0[m] = blank;
+        if (key[m] != KEY_EMPTY) c0[m] = cell_of(p, sc, key[m]);
+        c1[m] = c0[m];
     }
-    if (i < n_slots) {
-        reinterpret_cast<uint2*>(cells)[i] = make_uint2(c0, c1);
-    } else if (i < n_slots + n_tail) {
-        cells[2u * n_slots + (i - n_slots)] = blank;  // image-mode tail, context.rs:38-39
+    if (p.image) {   // warp-uniform
+        // the slot at column 0 of a row owns cells (row,0),(row,1); cell (row,1) is where the row's stamp goes
+        uint32_t row = 0, col = 0;
+        if (i0 < n_slots) { row = i0 / p.KW; col = i0 - row * p.KW; }
+        row += p.row0;
+        bool stamped[RESOLVE_SLOTS], contested[RESOLVE_SLOTS];
+        uint32_t srow[RESOLVE_SLOTS];
+        bool any_contested = false;
+#pragma unroll
+        for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m) {
+            while (col >= p.KW) { col -= p.KW; ++row; }
+            srow[m] = row;
+            stamped[m] = i0 + 32u * m < n_slots && col == 0u && q.rowmax[row] != 0u;
+            contested[m] = stamped[m] && key[m] != KEY_EMPTY;
+            any_contested |= contested[m];
+            col += 32u;
+        }
+        if (__any_sync(0xFFFFFFFFu, any_contested)) {
+#pragma unroll
+            for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m) {
+                const bool nl = stamp_beats_fragment(p, sc, q, contested[m], srow[m], key_tri(key[m]));
+                if (contested[m] && !nl) stamped[m] = false;   // the wrapped fragment was written after the last stamp
+            }
+        }
+#pragma unroll
+        for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m)
+            if (stamped[m]) c1[m] = (uint32_t)'\n';
     }
+#pragma unroll
+    for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m) {
+        const uint32_t i = i0 + 32u * m;
+        if (i < n_slots) reinterpret_cast<uint2*>(cells)[i] = make_uint2(c0[m], c1[m]);
+    }
+    // image-mode tail, context.rs:38-39
+    for (uint32_t j = tid; j < n_tail; j += gridDim.x * blockDim.x) cells[2u * n_slots + j] = blank;
 }
 
 SLOTH_DEV bool frag_later(const FrameParams& p, unsigned long long ka, uint32_t ida, unsigned long long kb,

@@ -2,15 +2,22 @@
 //
 // Same job as k_geom3 (draw_triangle's prologue and candidate loop, rasterizer.rs:56-91, for every triangle of the
 // scene), restructured around the per-vertex stage: k_xform has already applied Triangle::mul to every unique
-// vertex, so a triangle costs one 16-byte record load plus three 8-byte gathers of (x', y') from an L2-resident
-// array instead of nine coordinate loads and 36 un-fusable multiplies/adds.
+// vertex, so a triangle costs one 16-byte record plus three 8-byte gathers of (x', y') instead of nine coordinate
+// loads and 36 un-fusable multiplies/adds.
 //
-// Persistent warps, lane = triangle, chunk i -> warp i mod n_warps, two-deep software pipeline (record of chunk
-// k+2 and gathers of chunk k+1 in flight while chunk k is computed):
+// Persistent warps, lane = triangle, chunk i -> warp i mod n_warps.  The memory pipeline runs through shared memory
+// with cp.async (LDGSTS), every lane copying into slots only it reads, so no registers are held by loads in
+// flight, nothing hangs on the six scoreboards, and the depth is what the latency needs (the register-pipelined
+// predecessors of this kernel measured ~0.64 IPC with a third of the warp time in long-scoreboard waits):
+//   iteration k:  wait until the copies of iteration k-2 have landed
+//                 read record k+2 from its ring slot, start the three (x', y') gathers of chunk k+2
+//                 compute chunk k from its gathered coordinates
+//                 start the copy of record k+4
 //   A  bounds (aabb, rasterizer.rs:58-66), image-mode row stamps (32-row window per chunk, one REDUX.MIN +
-//      one REDUX.OR + one shared-memory ATOMS.MAX), back-face proof with a per-frame distance bound
+//      one REDUX.OR + one shared-memory ATOMS.MAX), back-face proof with a per-frame distance bound; chunks
+//      that are entirely back-facing (the far side of a closed mesh) end here
 //   B  2 x 3 lockstep footprint for triangles of at most 2 rows x 2 tight columns (separable edge terms)
-//   C  covered FRAGMENTS (not triangles) are parked in a per-warp shared-memory ring: (i0, i1, i2, triangle,
+//   C  covered FRAGMENTS (not triangles) are parked in a per-warp shared-memory ring (i0, i1, i2, triangle,
 //      x | y << 16); every 32 of them are emitted with all lanes busy -- gather (x', y', z') of the three
 //      vertices, normal / 1/area / depth / glyph, one 64-bit atomicMin into the key plane
 // Larger triangles: up to 8 x 8 candidates one lane each, beyond that row-band items for k_tail; non-finite or
@@ -23,26 +30,66 @@ namespace sloth {
 
 static constexpr uint32_t T_WARPS = 8;     // warps per block
 #ifndef T_BLOCKS_PER_SM
-#define T_BLOCKS_PER_SM 4
+#define T_BLOCKS_PER_SM 3      // persistent blocks per SM (shared memory: 3 x 60 KB)
+#endif
+#ifndef T_REG_BLOCKS
+#define T_REG_BLOCKS 3         // register budget = 65536 / (256 * T_REG_BLOCKS)
 #endif
 static constexpr uint32_t T_RING = 64;     // per-warp ring of covered fragments (power of two, >= 2 * 32)
+static constexpr uint32_t T_STAGES = 4;     // ring depth of the cp.async pipeline (records and coordinates)
 
 struct TRing {
+    uint32_t i0[T_RING], i1[T_RING], i2[T_RING];
     uint32_t tri[T_RING];
     uint32_t xy[T_RING];      // x | y << 16
 };
 
-// Emit `count` parked fragments starting at ring position `head`, lane = fragment: the triangle's record and its
-// three transformed vertices are gathered again (L1 / L2 hits: the warp touched them a chunk or two ago).
+// per-warp landing zone of the cp.async pipeline; lane l only ever touches [..][l]
+struct TPipe {
+    uint4 rec[T_STAGES][32];        // 512 B per stage
+    float2 xy[T_STAGES][3][32];     // 768 B per stage
+};
+
+struct TWarpSmem {
+    TPipe pipe;
+    TRing ring;
+};
+
+// smem_dst: 32-bit shared-window address
+SLOTH_DEV void cp_async8(uint32_t smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc));
+}
+SLOTH_DEV void cp_async16(uint32_t smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+SLOTH_DEV uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+SLOTH_DEV float2 lds64f(uint32_t a)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+SLOTH_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+SLOTH_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Emit `count` parked fragments starting at ring position `head`, lane = fragment.
 SLOTH_DEV void t_emit(const FrameParams& p, const Scene& sc, const TRing& wq, uint32_t head, uint32_t count, uint32_t lane,
                       unsigned long long* __restrict__ keys)
 {
     if (lane >= count || (p.debug & 8u)) return;
     const uint32_t slot = (head + lane) & (T_RING - 1u);
+    const uint32_t i0 = wq.i0[slot], i1 = wq.i1[slot], i2 = wq.i2[slot];
+    const float2 P1 = __ldg(sc.vxy + i0), P2 = __ldg(sc.vxy + i1), P3 = __ldg(sc.vxy + i2);
+    const float z1 = __ldg(sc.vz + i0), z2 = __ldg(sc.vz + i1), z3 = __ldg(sc.vz + i2);
     const uint32_t tri = wq.tri[slot], xy = wq.xy[slot];
-    const uint4 r = __ldg(sc.rec + tri);
-    const float2 P1 = __ldg(sc.vxy + r.x), P2 = __ldg(sc.vxy + r.y), P3 = __ldg(sc.vxy + r.z);
-    const float z1 = __ldg(sc.vz + r.x), z2 = __ldg(sc.vz + r.y), z3 = __ldg(sc.vz + r.z);
     Setup s;
     s.x1 = P1.x; s.y1 = P1.y; s.z1 = z1;
     s.x2 = P2.x; s.y2 = P2.y; s.z2 = z2;
@@ -59,27 +106,32 @@ SLOTH_DEV void t_emit(const FrameParams& p, const Scene& sc, const TRing& wq, ui
     emit_fragment(p, s, sh, tri, x, y, w0, w1, w2, keys);
 }
 
+// Dynamic shared memory of one block: [rowmax copy (ROWMAX_SHARED)] [TWarpSmem x T_WARPS]
+SLOTH_DEV size_t t_rowmax_words(uint32_t H) { return ((H + 31u) & ~31u) + 64u; }
+
 // ROWMAX_SHARED: the per-block copy of rowmax lives in dynamic shared memory (frames up to ~8 K rows), so the row
 // stamps are shared-memory atomics (ATOMS) instead of generic ones.
 template <bool CHECK_REGULAR, bool BAND, bool ROWMAX_SHARED>
-__global__ void __launch_bounds__(T_WARPS * 32, T_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(T_WARPS * 32, T_REG_BLOCKS)
 k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long* __restrict__ keys, const Queues q)
 {
-    __shared__ TRing rings[T_WARPS];
-    extern __shared__ __align__(16) uint32_t s_rowmax[];
+    extern __shared__ __align__(16) unsigned char t_smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    TRing& wq = rings[warp];
+    const uint32_t n_rowmax = (uint32_t)t_rowmax_words(p.H);
+    uint32_t* const s_rowmax = reinterpret_cast<uint32_t*>(t_smem);
+    TWarpSmem& ws = reinterpret_cast<TWarpSmem*>(t_smem + (ROWMAX_SHARED ? n_rowmax * 4u : 0u))[warp];
+    TRing& wq = ws.ring;
     const uint32_t n_chunks = (p.n_tri + 31u) >> 5;
     const uint32_t n_warps = gridDim.x * T_WARPS;
     const uint32_t gw = blockIdx.x * T_WARPS + warp;
     uint32_t q_head = 0, q_count = 0, nfrag_count = 0, chunks_done = 0;   // warp-uniform
     const bool do_stamps = p.image && !(p.debug & 2u);
-    const uint32_t n_rowmax = ((p.H + 31u) & ~31u) + 64u;
     if (ROWMAX_SHARED && do_stamps)
         for (uint32_t i = threadIdx.x; i < n_rowmax; i += blockDim.x) s_rowmax[i] = 0u;
     __syncthreads();
+    const uint32_t rowmax_a = smem_u32(s_rowmax);
     auto stamp = [&](uint32_t row, uint32_t value) {
-        if (ROWMAX_SHARED) atomicMax(s_rowmax + row, value);
+        if (ROWMAX_SHARED) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(rowmax_a + row * 4u), "r"(value) : "memory");
         else atomicMax(q.rowmax + row, value);
     };
 
@@ -91,45 +143,58 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
         const float R = add(mul(s.w, p.cull_scale), p.cull_pad);
         return sub(yc, R) >= (float)p.row1 || add(add(yc, R), 2.0f) <= (float)p.krow0;
     };
-    auto next_live = [&](uint32_t idx) -> uint32_t {   // next chunk of this warp after idx that is not culled
-        do idx += n_warps; while (BAND && idx < n_chunks && culled(idx));
-        return idx;
-    };
-    const uint32_t last = n_chunks ? n_chunks - 1u : 0u;
-    const uint32_t pf_dist = p.pf_chunks * n_warps;   // L2 prefetch distance of the record stream (0 = off)
-    // Software pipeline, two chunks deep, without register rotation: the loop body exists twice, once per
-    // coordinate set (A, B).  While set A's chunk is computed, set B's gathers (the chunk after it) are in flight;
-    // as soon as A's coordinates are dead the gathers of the chunk after B's are issued into A, and the record
-    // register is refilled with the record of the chunk after that.  Chunk indices past the end are clamped to
-    // the last chunk (valid memory, results unused).
-    // A record is read as 8 + 4 bytes: a 16-byte load would leave its unused last word to the register allocator,
-    // which hands it to the next instruction -- and that instruction then waits for the whole load.
-    struct Rec { uint32_t x, y, z; };
-    auto load_rec = [&](uint32_t chunk) -> Rec {
-        const uint4* r = sc.rec + min(chunk, last) * 32u + lane;
-        const uint2 a = __ldcs(reinterpret_cast<const uint2*>(r));
-        const uint32_t b = __ldcs(reinterpret_cast<const uint32_t*>(r) + 2);
-        return Rec{a.x, a.y, b};
-    };
-    uint32_t cA = gw;
-    if (BAND) while (cA < n_chunks && culled(cA)) cA += n_warps;
-    uint32_t cB = next_live(cA);
-    uint32_t cN = next_live(cB);   // the chunk whose record is in rn
-    Rec rn = load_rec(cA);
-    float2 A1 = __ldg(sc.vxy + rn.x), A2 = __ldg(sc.vxy + rn.y), A3 = __ldg(sc.vxy + rn.z);
-    rn = load_rec(cB);
-    float2 B1 = __ldg(sc.vxy + rn.x), B2 = __ldg(sc.vxy + rn.y), B3 = __ldg(sc.vxy + rn.z);
-    rn = load_rec(cN);
 
-    auto body = [&](float2& P1, float2& P2, float2& P3, uint32_t& c_set) {
-        const uint32_t c = c_set;
+    // This warp's chunks: gw, gw + n_warps, ...  (n_iter of them).  Ring slot of iteration k: k & 3, so the slots
+    // of k + 2 and k + 4 are one XOR away.  Band contexts keep `live`, a shift register over the next five
+    // iterations (bit j <-> iteration k + j: not culled): only live chunks are copied, gathered and computed.
+    // Past the end the record copies are clamped to the warp's last chunk (valid memory, results unused).
+    const uint32_t n_iter = gw < n_chunks ? (n_chunks - gw + n_warps - 1u) / n_warps : 0u;
+    const uint32_t rec_a = smem_u32(&ws.pipe.rec[0][lane]), xy_a = smem_u32(&ws.pipe.xy[0][0][lane]);
+    const uint4* const rec_g = sc.rec + (size_t)gw * 32u + lane;
+    const uint32_t rec_step = n_warps * 32u;   // records between consecutive chunks of this warp
+    auto is_live = [&](uint32_t k) -> uint32_t {
+        if (!BAND) return 1u;
+        return (k < n_iter && !culled(gw + k * n_warps)) ? 1u : 0u;
+    };
+    auto fetch_rec = [&](uint32_t k, uint32_t slot) {   // record of iteration k -> ring slot
+        cp_async16(rec_a + (slot << 9), rec_g + (size_t)min(k, n_iter - 1u) * rec_step);
+    };
+    auto gather_xy = [&](uint32_t slot) {   // (x', y') of the three corners of the record in ring slot `slot`
+        const uint4 r = lds128(rec_a + (slot << 9));
+        cp_async8(xy_a + slot * 768u, sc.vxy + r.x);
+        cp_async8(xy_a + slot * 768u + 256u, sc.vxy + r.y);
+        cp_async8(xy_a + slot * 768u + 512u, sc.vxy + r.z);
+    };
+    uint32_t live = 0;
+    if (n_iter) {
+        for (uint32_t j = 0; j < 4u; ++j) {
+            const uint32_t l = is_live(j);
+            live |= l << j;
+            if (l) fetch_rec(j, j);
+        }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    if (n_iter && (live & 1u)) gather_xy(0u);
+    cp_async_commit();
+    if (n_iter && (live & 2u)) gather_xy(1u);
+    cp_async_commit();
+
+    for (uint32_t k = 0; k < n_iter; ++k) {
+        const uint32_t c = gw + k * n_warps;
+        const uint32_t ps = k & 3u;   // ring slot of this iteration's record and coordinates
+        cp_async_wait<1>();   // everything committed two iterations ago has landed: coordinates k, record k + 2
+        if (!BAND || (live & 4u)) gather_xy(ps ^ 2u);
+        uint32_t mask = 0, minx = 0, miny = 0;
         const uint32_t t = c * 32u + lane;
+        if (!BAND || (live & 1u)) {
         if (p.count_frags) ++chunks_done;
+        const float2 P1 = lds64f(xy_a + ps * 768u), P2 = lds64f(xy_a + ps * 768u + 256u), P3 = lds64f(xy_a + ps * 768u + 512u);
         const float x1 = P1.x, y1 = P1.y, x2 = P2.x, y2 = P2.y, x3 = P3.x, y3 = P3.y;
 
         // ---- phase A: bounds (Triangle::aabb, rasterizer.rs:58-66) ----------------------------
         const float mn1 = fminf(y1, fminf(y2, y3)), mx1 = fmaxf(y1, fmaxf(y2, y3));
-        const uint32_t miny = __float2uint_rz(ceilf(fmaxf(mn1, 1.0f)));
+        miny = __float2uint_rz(ceilf(fmaxf(mn1, 1.0f)));
         const uint32_t maxy = __float2uint_rz(ceilf(fminf(mx1, p.hm1)));
         // padding triangles sit on the sentinel vertex (-1e30): maxy = 0, no rows
         const bool has_rows = miny < maxy && (!BAND || (miny < p.row1 && maxy + 1u > p.krow0));
@@ -169,7 +234,6 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
         }
         // chunks on the far side of a closed mesh end here (after the stamps); so do empty ones
         const bool maybe = has_rows && (CHECK_REGULAR ? (!regular || !back) : !back) && !(p.debug & 16u);
-        uint32_t mask = 0, minx = 0;
         if (__any_sync(0xFFFFFFFFu, maybe || tall)) {
             minx = __float2uint_rz(ceilf(fmaxf(mn0, 1.0f)));
             const uint32_t maxx = __float2uint_rz(ceilf(fminf(mul(mx0, 2.0f), p.wm1)));
@@ -265,6 +329,8 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
                     const unsigned who = __ballot_sync(0xFFFFFFFFu, has);
                     if (has) {
                         const uint32_t slot = (q_head + q_count + __popc(who & ((1u << lane) - 1u))) & (T_RING - 1u);
+                        const uint4 r = lds128(rec_a + (ps << 9));
+                        wq.i0[slot] = r.x; wq.i1[slot] = r.y; wq.i2[slot] = r.z;
                         wq.tri[slot] = t;
                         wq.xy[slot] = (minx + (bit & 7u)) | ((miny + (bit >> 3)) << 16);
                     }
@@ -311,15 +377,7 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
             }
         }
 
-        // ---- the coordinates of this chunk are dead: this set takes the chunk whose record is in rn (its
-        // gathers have a whole body of the other set to land), the record register moves one chunk on.
-        P1 = __ldg(sc.vxy + rn.x); P2 = __ldg(sc.vxy + rn.y); P3 = __ldg(sc.vxy + rn.z);
-        c_set = cN;
-        cN = next_live(cN);
-        rn = load_rec(cN);
-        // ... and the record lines a few chunks further on are pulled into L2: one 512-byte load per warp in
-        // flight cannot keep HBM busy (Little's law), the prefetches cost no registers
-        if (pf_dist) asm volatile("prefetch.global.L2 [%0];" ::"l"(sc.rec + min(cN + pf_dist, last) * 32u + lane));
+        }   // live chunk
 
         // ---- phase C: park the covered fragments of the 2 x 3 footprint, one per lane and turn; every 32
         // parked fragments are emitted with all lanes busy ---------------------------------------------
@@ -331,6 +389,8 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
             const unsigned who = __ballot_sync(0xFFFFFFFFu, has);
             if (has) {
                 const uint32_t slot = (q_head + q_count + __popc(who & ((1u << lane) - 1u))) & (T_RING - 1u);
+                const uint4 r = lds128(rec_a + (ps << 9));
+                wq.i0[slot] = r.x; wq.i1[slot] = r.y; wq.i2[slot] = r.z;
                 wq.tri[slot] = t;
                 wq.xy[slot] = xy0 + bit + (bit >= 3u ? 65536u - 3u : 0u);   // bit = row * 3 + column
             }
@@ -345,13 +405,19 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
             }
         }
 
-    };
-    for (;;) {
-        if (cA >= n_chunks) break;
-        body(A1, A2, A3, cA);
-        if (cB >= n_chunks) break;
-        body(B1, B2, B3, cB);
+
+        // ---- record of iteration k + 4 (same ring slot as record k, which the parking above was the last to
+        // read), then one commit for everything this iteration started
+        if (BAND) {
+            const uint32_t l = is_live(k + 4u);
+            live = (live >> 1) | (l << 3);
+            if (l) fetch_rec(k + 4u, ps);
+        } else {
+            fetch_rec(k + 4u, ps);
+        }
+        cp_async_commit();
     }
+    cp_async_wait<0>();
     if (q_count) {
         __syncwarp();
         t_emit(p, sc, wq, q_head, q_count, lane, keys);
