@@ -16,12 +16,18 @@ frame: update + clear + draw_mesh over the whole scene (main.rs:78-83).
 * e2e       the same frames through the public C-ABI call with HOST buffers
             (sloth_render_batch: per frame the rotation goes host->device, the cell buffer comes
             back device->host into pinned memory), wall clock, max over ranks.
-* roofline  dominant kernel k_geom3 (reads the whole scene): algorithmic 40 B/triangle / its average
-            duration (CUDA events recorded inside the library around that kernel, one frame per
-            sample, same frames as the timed region) against the measured HBM peak.
+* roofline  dominant kernel (k_tri on the indexed path, k_geom3 on the soup path; it visits every triangle
+            of the scene): algorithmic 40 B/triangle / its average duration (CUDA events recorded inside
+            the library around that kernel, one frame per sample, same frames as the timed region)
+            against the measured HBM peak; `frame_frac` is the whole frame (40 N + 4 W H bytes over the
+            batch time per frame) against the same peak.
+* post_check  after the timed batch the last frame it left on the device is compared with a single
+            sloth_render_device of the same rotation (and hashed): the timed path is verified at size.
 * cpu_baseline / --impl reference: the CPU oracle (oracle/sloth_oracle.c, a port: the Rust reference
             cannot be built in this image), timed on a bounded sample (every S-th triangle) and
-            scaled to frames/s; the oracle is only ever the thing *compared against*.
+            scaled to frames/s.  The reference is single-threaded, so `value` is the ONE-thread figure;
+            a frames-across-cores run is reported beside it (`all_cores`).  That arm touches nothing of
+            the product library: rotations and angles come from the oracle.
 Multi-GPU: frames are independent -> rank r renders frames r, r+N, ... ("weak": K frames per rank).
 """
 import argparse
@@ -46,17 +52,40 @@ def log(*a):
 
 
 def make_scene(freq):
-    from rust_sloth_b200 import meshes
-    t = time.time()
-    xyz, rgb, s0 = meshes.icosphere(freq)
-    log(f"[bench] icosphere f={freq}: {len(xyz)} triangles in {time.time() - t:.1f}s")
-    return xyz, rgb, s0
+    return icosphere_soup(freq)
 
 
 def rotations(n):
+    """main.rs:55-58,76-77,92-96 through the product's host helpers (the b200 arm)."""
     import rust_sloth_b200 as rs
     pitches = rs.turntable_pitches(0.0, n)
     return np.stack([rs.rotation_from_euler(0.0, p, 0.0) for p in pitches])
+
+
+def rotations_oracle(n):
+    """The same sequence from the oracle (the reference arm must not load the product library)."""
+    import oracle
+    return np.stack([oracle.rotation(0.0, p, 0.0) for p in oracle.turntable(0.0, n)])
+
+
+def workload_config(n_tri, freq, world):
+    """`config` of the JSON line -- one function for both arms, so the two dicts are identical."""
+    return {"workload": f"icosphere f={freq} ({n_tri} triangles) at {WIDTH}x{HEIGHT}, image mode, "
+                        f"{TURNTABLE_FRAMES}-frame turntable angles",
+            "l2": "inputs exceed L2 (10 M triangles streamed per frame), no flush",
+            "sharding": "independent frames per GPU, no collective" if world > 1 else "single GPU"}
+
+
+def icosphere_soup(freq):
+    """meshes.icosphere without importing the product package's __init__ (reference arm)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_sloth_meshes", os.path.join(ROOT, "rust-sloth_b200", "meshes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    t = time.time()
+    xyz, rgb, s0 = mod.icosphere(freq)
+    log(f"[bench] icosphere f={freq}: {len(xyz)} triangles in {time.time() - t:.1f}s")
+    return xyz, rgb, s0
 
 
 class ClockSampler:
@@ -134,51 +163,59 @@ def cpu_sample(xyz, rgb, s0, rot, target_s=12.0):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port), all host threads, one frame
-    sample per thread per step."""
+    """--impl reference: the reference's CPU algorithm (oracle port).  Each timed step is one frame sample
+    (every S-th triangle over the reference's full scan domain) on ONE thread -- the reference is single-threaded;
+    afterwards one frames-across-cores pass (a sample per host thread) gives the all-cores figure."""
     if rank != 0:
         return
     import oracle
     from concurrent.futures import ThreadPoolExecutor
-    xyz, rgb, s0 = make_scene(args.freq)
-    rots = rotations(TURNTABLE_FRAMES)
+    xyz, rgb, s0 = icosphere_soup(args.freq)
+    rots = rotations_oracle(TURNTABLE_FRAMES)
     threads = max(1, len(os.sched_getaffinity(0)))
-    # one step = one frame sample per thread; size it so that warmup+steps stay within ~2.5 minutes
-    step_target = min(args.ref_step_seconds, 150.0 / max(1, args.steps + args.warmup))
+    # size a step so that warmup+steps (one thread) plus the all-cores pass stay within ~2.5 minutes
+    step_target = min(args.ref_step_seconds, 120.0 / max(1, args.steps + args.warmup + 2))
     stride, t_clear = cpu_sample(xyz, rgb, s0, rots[0], target_s=step_target)
-    log(f"[bench/reference] {threads} threads, every {stride}-th triangle per frame sample, clear {t_clear * 1e3:.0f} ms")
+    log(f"[bench/reference] every {stride}-th triangle per frame sample, clear {t_clear * 1e3:.0f} ms, {threads} host threads")
 
     def one(i):
         _, _, cnt = oracle.render(xyz, rgb, s0, WIDTH, HEIGHT, rots[i % len(rots)], mode=0,
                                   tri_first=i % stride, tri_step=stride)
         return cnt["covered"]
 
-    pool = ThreadPoolExecutor(threads)
     k = 0
     for _ in range(args.warmup):
-        list(pool.map(one, range(k, k + threads)))
-        k += threads
+        one(k)
+        k += 1
     t0 = time.perf_counter()
     covered = 0
     for _ in range(args.steps):
-        covered += sum(pool.map(one, range(k, k + threads)))
-        k += threads
-    dt = time.perf_counter() - t0
-    t_step = dt / args.steps                       # `threads` frame samples in parallel
-    t_frame = t_clear + stride * max(t_step - t_clear, 1e-9)   # one full frame on one thread
-    fps = threads / t_frame
-    frags_per_frame = covered * stride / (args.steps * threads)
-    sample = (f"each step = {threads} concurrent frame samples (one per host thread), a sample = every {stride}-th "
-              f"triangle of the {len(xyz)}-triangle frame over the reference's full scan domain; "
-              f"frames/s = threads / (t_clear + {stride} * (t_step - t_clear))")
+        covered += one(k)
+        k += 1
+    t_step = (time.perf_counter() - t0) / args.steps
+    t_frame = t_clear + stride * max(t_step - t_clear, 1e-9)     # one full frame on one thread
+    fps = 1.0 / t_frame
+    frags_per_frame = covered * stride / args.steps
+    # all host cores: one frame sample per thread, concurrently (frames are independent)
+    pool = ThreadPoolExecutor(threads)
+    list(pool.map(one, range(k, k + threads)))
+    k += threads
+    t0 = time.perf_counter()
+    list(pool.map(one, range(k, k + threads)))
+    t_par = time.perf_counter() - t0
+    fps_all = threads / (t_clear + stride * max(t_par - t_clear, 1e-9))
+    sample = (f"each step = one frame sample on one thread, a sample = every {stride}-th triangle of the "
+              f"{len(xyz)}-triangle frame over the reference's full scan domain; "
+              f"frames/s = 1 / (t_clear + {stride} * (t_step - t_clear))")
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_frame * 1e3 / threads,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_frame * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "gfragments_per_s": frags_per_frame * fps / 1e9,
-        "config": {"workload": f"icosphere f={args.freq} ({len(xyz)} triangles) at {WIDTH}x{HEIGHT}, image mode, "
-                               f"{TURNTABLE_FRAMES}-frame turntable angles"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": workload_config(len(xyz), args.freq, world),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port", "sample": sample},
+        "all_cores": {"value": fps_all, "unit": "frames/s", "cores": threads,
+                      "sample": f"{threads} concurrent frame samples, one per host thread, same sampling"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -249,16 +286,43 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
 
+    # ---- post-check: the frame the timed batch left on the device == a single render of that rotation ----
+    import hashlib
+    d_check = torch.empty(cpf + 2, dtype=torch.int32, device=f"cuda:{local_rank}")
+    ctx.render_device(timed_rots[-1], d_check.data_ptr())
+    ctx.sync()
+    same = bool(torch.equal(d_cells[:cpf], d_check[:cpf]))
+    post_check = {"last_timed_frame_equals_single_render": same,
+                  "cells_sha256": hashlib.sha256(d_cells[:cpf].cpu().numpy().tobytes()).hexdigest(),
+                  "frame": int(my_frames[-1])}
+    del d_check
+
     # ---- roofline: per-kernel events, one frame per sample --------------------------------
     ctx.stats_enable(kernel_timing=True)
-    geom_ms, walk_ms, resolve_ms, frame_ms = [], [], [], []
+    geom_ms, xform_ms, walk_ms, resolve_ms, frame_ms = [], [], [], [], []
     for f in my_frames[Wm:]:
         ctx.render_device(rots[f], d_cells.data_ptr())
         st = ctx.stats()
-        geom_ms.append(st["geom_ms"]); walk_ms.append(st["walk_ms"])
+        geom_ms.append(st["geom_ms"]); walk_ms.append(st["walk_ms"]); xform_ms.append(st["xform_ms"])
         resolve_ms.append(st["resolve_ms"]); frame_ms.append(st["last_frame_ms"])
     last = ctx.stats()
     ctx.stats_enable()
+    indexed = last["geom_path"] == rs.PATH_INDEXED
+    kernel_name = "k_tri" if indexed else "k_geom3"
+
+    # ---- bare device->host ceiling: the same bytes per frame, nothing else running on this GPU (all ranks at once)
+    d2h_pin = torch.empty(cpf, dtype=torch.int32, pin_memory=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        d2h_pin.copy_(d_cells[:cpf], non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(16):
+        d2h_pin.copy_(d_cells[:cpf], non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    d2h_ms = e0.elapsed_time(e1) / 16
+    del d2h_pin
 
     # ---- e2e: public API, host buffers ------------------------------------------------------
     ring = max(1, min(K, 64))   # page-locked frames (2.1 GB at 4K); a larger K reuses them, 64 frames per call
@@ -272,10 +336,10 @@ def run_b200(args, rank, local_rank, world):
     e2e_s = time.perf_counter() - t0
     barrier()
 
-    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
+    times = torch.tensor([dev_ms, e2e_s * 1e3, d2h_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(times[0]), float(times[1])
+    dev_ms_max, e2e_ms_max, d2h_ms_max = float(times[0]), float(times[1]), float(times[2])
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -285,32 +349,41 @@ def run_b200(args, rank, local_rank, world):
             hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         g_ms = float(np.mean(geom_ms))
         achieved = 40.0 * n_tri / (g_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM traffic of the dominant kernel: not measurable outside ncu, so it is the figure of the committed
+        # `ncu --set full` capture, labelled with the commit it was taken at (profiles/traffic.json)
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("k_geom3_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get(f"{kernel_name}_dram_bytes_per_launch")
+            traffic_src = f"{tj.get('capture', 'ncu --set full')} at commit {tj.get('commit', '?')}"
         fps = K * world / (dev_ms_max * 1e-3)
         e2e_fps = K * world / (e2e_ms_max * 1e-3)
+        d2h_ceiling_fps = world / (d2h_ms_max * 1e-3)
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "gfragments_per_s": frags_per_frame * fps / 1e9,
             "fragments_per_frame": frags_per_frame,
-            "config": {"workload": f"icosphere f={args.freq} ({n_tri} triangles) at {WIDTH}x{HEIGHT}, image mode, "
-                                   f"{TURNTABLE_FRAMES}-frame turntable angles",
-                       "l2": "inputs exceed L2 (401 MB scene streamed per frame), no flush",
-                       "sharding": "independent frames per GPU, no collective" if world > 1 else "single GPU"},
+            "config": workload_config(n_tri, args.freq, world),
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": cpf * 4,
-                    "gfragments_per_s": frags_per_frame * e2e_fps / 1e9},
-            "roofline": {"bound": "hbm", "kernel": "k_geom3", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                    "gfragments_per_s": frags_per_frame * e2e_fps / 1e9,
+                    # the end-to-end number has its own roofline: the measured device->host rate of the same bytes
+                    "d2h_gbs_measured": cpf * 4 * world / (d2h_ms_max * 1e-3) / 1e9,
+                    "d2h_ceiling_frames_per_s": d2h_ceiling_fps, "frac_of_d2h_ceiling": e2e_fps / d2h_ceiling_fps},
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": 40 * n_tri, "avg_launch_ms": g_ms,
                          "frame_bytes": 40 * n_tri + 4 * WIDTH * HEIGHT,
                          "frame_frac": (40.0 * n_tri + 4.0 * WIDTH * HEIGHT) / (dev_ms_max / K * 1e-3) / 1e9 / hbm_peak,
-                         "kernel_ms": {"k_geom3": g_ms, "k_tail": float(np.mean(walk_ms)),
+                         "kernel_ms": {kernel_name: g_ms, "k_xform": float(np.mean(xform_ms)),
+                                       "k_tail": float(np.mean(walk_ms)),
                                        "k_resolve": float(np.mean(resolve_ms)),
-                                       "frame_unoverlapped": float(np.mean(frame_ms))}},
+                                       "frame_unoverlapped": float(np.mean(frame_ms))},
+                         "geometry_path": "indexed" if indexed else "soup", "unique_vertices": int(last["n_vert"])},
+            "post_check": post_check,
             "gpu_launches": int(launches_timed),
             "clocks": clk.summary(t_wall0, t_wall1),
             "last_frame_stats": {k: last[k] for k in ("walk_tris", "walk_items", "irregular_tris", "stamp_fixups")},

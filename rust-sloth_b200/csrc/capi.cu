@@ -711,7 +711,8 @@ int build_index(sloth_ctx* c, size_t n_tri)
         const size_t n_padded = (n_tri + 31) & ~(size_t)31;
         ix::k_ix_records<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(rep, rank, (uint32_t)n_tri, (uint32_t)n_padded, n_vert,
                                                                                   c->sc_rec);
-        c->launches += 2;
+        ix::k_ix_connectivity<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(c->sc_rec, (uint32_t)n_tri, (uint32_t)(n_padded / 32));
+        c->launches += 3;
         CU_IX(cudaGetLastError());
         CU_IX(cudaStreamSynchronize(c->stream));
         c->indexed = true;

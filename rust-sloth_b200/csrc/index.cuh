@@ -202,6 +202,37 @@ __global__ void __launch_bounds__(256) k_ix_records(const uint32_t* __restrict__
     rec[t] = make_uint4(rank[rep[3u * t]], rank[rep[3u * t + 1u]], rank[rep[3u * t + 2u]], 0u);
 }
 
+// Connectivity flag of every chunk of 32 triangles (bit 0 of rec[..].w, same value in all 32 records): set when the
+// chunk is full and its triangles form one component under "share a vertex id".  k_tri then stamps the chunk's rows
+// as one interval.  One warp per chunk, lane = triangle: labels start as the lane index and take the minimum over
+// every triangle they share a vertex with, until nothing changes.
+__global__ void __launch_bounds__(256) k_ix_connectivity(uint4* __restrict__ rec, uint32_t n_tri, uint32_t n_chunks)
+{
+    const uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (chunk >= n_chunks) return;
+    const uint32_t t = chunk * 32u + lane;
+    uint4 r = rec[t];
+    const bool full = chunk * 32u + 32u <= n_tri;
+    uint32_t label = lane;
+    for (int round = 0; round < 32; ++round) {
+        const uint32_t before = label;
+        for (int s = 0; s < 32; ++s) {
+            const uint32_t ax = __shfl_sync(0xFFFFFFFFu, r.x, s), ay = __shfl_sync(0xFFFFFFFFu, r.y, s), az = __shfl_sync(0xFFFFFFFFu, r.z, s);
+            const uint32_t ls = __shfl_sync(0xFFFFFFFFu, label, s);
+            const bool share = r.x == ax || r.x == ay || r.x == az || r.y == ax || r.y == ay || r.y == az || r.z == ax || r.z == ay ||
+                               r.z == az;
+            if (share && ls < label) label = ls;
+            // the other direction: triangle s learns this lane's label in the same step
+            const uint32_t back = __reduce_min_sync(0xFFFFFFFFu, share ? label : 0xFFFFFFFFu);
+            if ((int)lane == s && back < label) label = back;
+        }
+        if (!__any_sync(0xFFFFFFFFu, label != before)) break;
+    }
+    const bool one = full && __all_sync(0xFFFFFFFFu, label == 0u);
+    r.w = one ? 1u : 0u;
+    rec[t] = r;
+}
+
 // sloth_scene_set_indexed: positions[indices[..]] (geometry.rs:99-107) -> the resident soup streams and colours;
 // ids are checked against n_vert (*bad counts the triangles that fail, they become all-zero triangles).
 __global__ void __launch_bounds__(256) k_ix_expand_input(const float* __restrict__ pos, uint32_t n_vert, const uint32_t* __restrict__ idx,

@@ -70,6 +70,12 @@ SLOTH_DEV uint4 lds128(uint32_t a)
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
+SLOTH_DEV uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
 SLOTH_DEV float2 lds64f(uint32_t a)
 {
     float2 v;
@@ -129,7 +135,9 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     if (ROWMAX_SHARED && do_stamps)
         for (uint32_t i = threadIdx.x; i < n_rowmax; i += blockDim.x) s_rowmax[i] = 0u;
     __syncthreads();
-    const uint32_t rowmax_a = smem_u32(s_rowmax);
+    uint32_t rowmax_a = smem_u32(s_rowmax);
+    asm volatile("" : "+r"(rowmax_a));   // keep the shared-window address in a register (the compiler would re-derive it
+                                         // from the CTA id with an S2UR at every use)
     auto stamp = [&](uint32_t row, uint32_t value) {
         if (ROWMAX_SHARED) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(rowmax_a + row * 4u), "r"(value) : "memory");
         else atomicMax(q.rowmax + row, value);
@@ -149,7 +157,8 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     // iterations (bit j <-> iteration k + j: not culled): only live chunks are copied, gathered and computed.
     // Past the end the record copies are clamped to the warp's last chunk (valid memory, results unused).
     const uint32_t n_iter = gw < n_chunks ? (n_chunks - gw + n_warps - 1u) / n_warps : 0u;
-    const uint32_t rec_a = smem_u32(&ws.pipe.rec[0][lane]), xy_a = smem_u32(&ws.pipe.xy[0][0][lane]);
+    uint32_t rec_a = smem_u32(&ws.pipe.rec[0][lane]), xy_a = smem_u32(&ws.pipe.xy[0][0][lane]);
+    asm volatile("" : "+r"(rec_a), "+r"(xy_a));
     const uint4* const rec_g = sc.rec + (size_t)gw * 32u + lane;
     const uint32_t rec_step = n_warps * 32u;   // records between consecutive chunks of this warp
     auto is_live = [&](uint32_t k) -> uint32_t {
@@ -204,7 +213,17 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
         // become bits of a 32-row window, one REDUX.OR, then lane i owns row first + i.
         const uint32_t sy0 = BAND ? max(miny, p.srow0) : miny, sy1 = BAND ? min(maxy, p.srow1) : maxy;
         bool tall = false;   // rows outside the window: stamped in the rare block
-        if (do_stamps) {
+        // A chunk whose 32 triangles hang together through shared vertices (flag in the record, set at scene-set)
+        // stamps exactly the rows [min miny, max maxy): the y-ranges of triangles that share a vertex overlap or
+        // touch, so the union of the chunk's ranges has no gap, and ceil() commutes with min / max.
+        const bool connected = !BAND && !CHECK_REGULAR && (lds32(rec_a + (ps << 9) + 12u) & 1u) != 0u;   // warp-uniform
+        if (do_stamps && connected) {
+            const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, miny);
+            const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, maxy);
+            if (lo + lane < hi) stamp(lo + lane, c + 1u);
+            if (lo + 32u < hi)   // taller than a warp (rare): the remaining rows, strided
+                for (uint32_t y = lo + 32u + lane; y < hi; y += 32u) stamp(y, c + 1u);
+        } else if (do_stamps) {
             const bool st = has_rows && (!BAND || sy0 < sy1);
             const uint32_t first = __reduce_min_sync(0xFFFFFFFFu, st ? sy0 : 0xFFFFFFFFu);
             const uint32_t lo = sy0 - first, n = sy1 - sy0;   // meaningful when st (then n >= 1)

@@ -407,17 +407,9 @@ def test_error_codes_and_call_order():
 
 
 def test_full_size_baseline_configs_bit_exact():
-    """BASELINE configs at their full size.  The 10M-triangle icosphere at 3840x2160 is checked against the
-    oracle's row-terminating mode (mode 1, itself validated against the faithful scan on every smaller case;
-    the faithful scan would take ~20 s here); 'suzy suzy' at 3840x2160 (every fragment of the second copy is
-    an exact depth tie) and skull at 1920x1080 against the faithful scan."""
-    xyz, rgb, s0 = meshes.icosphere(708)
-    assert len(xyz) == 10_025_280
-    rot = oracle.rotation(0.0, oracle.turntable(0.0, 64)[5], 0.0)
-    ocells, oz, ocnt = oracle.render(xyz, rgb, s0, 3840, 2160, rot, mode=1)
-    cells, z, st = gpu_frame(xyz, rgb, s0, 3840, 2160, rot)
-    assert_same(cells, z, ocells, oz, "icosphere f=708 4K")
-    assert st["fragments"] == ocnt["covered"]
+    """BASELINE configs at their full size: 'suzy suzy' at 3840x2160 (every fragment of the second copy is an exact
+    depth tie) and skull at 1920x1080 against the faithful scan.  (The 10M-triangle frame, the 360-frame turntable
+    and the two-model scene are in test_gpu_configs.py.)"""
     for scene, W, H in [("suzy_suzy", 3840, 2160), ("skull", 1920, 1080)]:
         xyz, rgb, s0 = S.soup(scene)
         rot = oracle.rotation(0.0, S.PI, 0.0)
