@@ -235,6 +235,11 @@ SLOTH_API size_t sloth_turntable_pitches(float y_arg, uint32_t n_frames, float *
  * overlap with rendering when the destination is pinned. */
 SLOTH_API int sloth_pinned_alloc(size_t bytes, void **out);
 SLOTH_API int sloth_pinned_free(void *ptr);
+/* Page-lock memory the caller already owns (cudaHostRegister) -- e.g. a POSIX shared-memory frame that the per-GPU
+ * processes of a box all map: in band mode every rank then passes `frame + row0*W` as cells_out of sloth_render and
+ * its band travels straight over its own PCIe link into the final host frame (no root GPU, no gather). */
+SLOTH_API int sloth_host_register(void *ptr, size_t bytes);
+SLOTH_API int sloth_host_unregister(void *ptr);
 /* number of cells per frame for this context: W*H (+H in image mode), or band size */
 SLOTH_API size_t sloth_cells_per_frame(const sloth_ctx *ctx);
 

@@ -49,7 +49,8 @@ ABI_SYMBOLS = [
     "sloth_render_batch", "sloth_render_device", "sloth_ctx_sync", "sloth_ctx_set_band",
     "sloth_shader_set", "sloth_stats_get", "sloth_stats_enable", "sloth_last_error",
     "sloth_rotation_from_euler", "sloth_utransform", "sloth_turntable_pitches", "sloth_cells_per_frame",
-    "sloth_pinned_alloc", "sloth_pinned_free", "sloth_ctx_stream", "sloth_render_device_batch",
+    "sloth_pinned_alloc", "sloth_pinned_free", "sloth_host_register", "sloth_host_unregister", "sloth_ctx_stream",
+    "sloth_render_device_batch",
     "sloth_text_capacity", "sloth_render_text", "sloth_render_text_batch", "sloth_flush_device",
     "sloth_scene_load", "sloth_loader_begin", "sloth_loader_add_obj", "sloth_loader_add_stl", "sloth_loader_commit",
     "sloth_scene_size", "sloth_scene_get",
@@ -127,6 +128,8 @@ def load_library() -> C.CDLL:
     L.sloth_cells_per_frame.restype = C.c_size_t
     L.sloth_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.sloth_pinned_free.argtypes = [vp]
+    L.sloth_host_register.argtypes = [vp, C.c_size_t]
+    L.sloth_host_unregister.argtypes = [vp]
     L.sloth_scene_load.argtypes = [vp, C.c_char_p, C.POINTER(C.c_size_t), fp]
     L.sloth_loader_begin.argtypes = [vp]
     L.sloth_loader_add_obj.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p]
@@ -147,6 +150,15 @@ def load_library() -> C.CDLL:
 
 
 IPC_HANDLE_BYTES = 64
+
+
+def host_register(array: np.ndarray) -> None:
+    """Page-lock memory the caller owns (e.g. a shared-memory frame mapped by every per-GPU process)."""
+    _check(load_library().sloth_host_register(C.c_void_p(array.ctypes.data), array.nbytes))
+
+
+def host_unregister(array: np.ndarray) -> None:
+    _check(load_library().sloth_host_unregister(C.c_void_p(array.ctypes.data)))
 
 
 def device_alloc(device: int, nbytes: int) -> int:
@@ -510,6 +522,12 @@ class Context:
     # -- direct entry points -----------------------------------------------------------
     def cells_per_frame(self) -> int:
         return int(self._L.sloth_cells_per_frame(self._h))
+
+    def render_into(self, rot: np.ndarray, out: np.ndarray) -> None:
+        """sloth_render straight into caller memory (cells_per_frame() uint32 cells, ideally page-locked)."""
+        rot = np.ascontiguousarray(rot, np.float32).reshape(16)
+        assert out.dtype == np.uint32 and out.flags.c_contiguous and out.size >= self.cells_per_frame()
+        _check(self._L.sloth_render(self._h, _fp(rot), out.ctypes.data_as(C.POINTER(C.c_uint32)), None))
 
     def render(self, rot: np.ndarray, want_z: bool = False):
         rot = np.ascontiguousarray(rot, np.float32).reshape(16)

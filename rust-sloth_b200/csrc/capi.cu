@@ -1380,6 +1380,19 @@ int sloth_pinned_free(void* ptr)
     return SLOTH_OK;
 }
 
+int sloth_host_register(void* ptr, size_t bytes)
+{
+    if (!ptr || !bytes) return fail(SLOTH_E_ARG, "ptr is null or bytes is 0");
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return SLOTH_OK;
+}
+
+int sloth_host_unregister(void* ptr)
+{
+    if (ptr) CU(cudaHostUnregister(ptr));
+    return SLOTH_OK;
+}
+
 /* ---- host-side helpers ---- */
 
 void sloth_utransform(uint32_t W, uint32_t H, float scene_max, float out[16])

@@ -14,6 +14,13 @@ that land in the band.  Two ways to put the bands together:
 ``allgather``
     Each rank resolves into a local buffer and one ``all_gather_into_tensor`` moves 4*W*H/N bytes per GPU.
 
+``host`` (:class:`HostBandRenderer`)
+    The frame's destination is the host anyway (``Context::flush`` reads it there), so no GPU collects it: the
+    ranks map one POSIX shared-memory frame, page-lock it (``sloth_host_register``) and every rank's
+    ``sloth_render`` copies its band over its own PCIe link to ``frame + e[r]*W``.  Completion is a per-rank
+    frame counter in the same shared segment (no collective, no NVLink traffic).  Band edges can follow the work:
+    :meth:`HostBandRenderer.rebalance` moves them to equal shares of the chunks each band processed.
+
 torch is only used for the process group, streams and (allgather mode) device memory.
 """
 from __future__ import annotations
@@ -143,3 +150,84 @@ class BandRenderer:
         if image:
             cells = np.concatenate([cells, np.full(self.H, ord(" "), np.uint32)])
         return cells
+
+
+class HostBandRenderer:
+    """Row bands assembled in a page-locked shared-memory host frame; one process per GPU.
+
+    ``name`` identifies the shared segment (rank 0 creates it).  ``render(rot)`` returns when this rank's band is
+    in the frame; ``wait(k)`` (any rank, usually the consumer on rank 0) returns when all bands of frame k are."""
+
+    HEADER = 4096   # bytes: per-rank frame counters (uint64), then the frame
+
+    def __init__(self, ctx, width: int, height: int, rank: int, world: int, name: str, barrier=None, edges=None,
+                 page_lock: bool = True):
+        from multiprocessing import shared_memory
+        from . import host_register
+        self.page_lock = page_lock
+        self.ctx, self.W, self.H, self.rank, self.world = ctx, width, height, rank, world
+        self.barrier = barrier or (lambda: None)
+        self.frame_cells = width * height + height
+        nbytes = self.HEADER + 4 * self.frame_cells
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=nbytes)
+            self.shm.buf[:self.HEADER] = bytes(self.HEADER)
+        self.barrier()
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name)
+        self.counters = np.ndarray((world,), np.uint64, self.shm.buf, 0)
+        self.frame = np.ndarray((self.frame_cells,), np.uint32, self.shm.buf, self.HEADER)
+        self._whole = np.ndarray((nbytes,), np.uint8, self.shm.buf, 0)
+        if page_lock:
+            host_register(self._whole)
+        if rank == 0:
+            self.frame[width * height:] = ord(" ")          # image-mode tail, context.rs:38-39
+        ctx.resize(width, height)
+        self.k = 0
+        self.set_edges(edges or band_edges(height, world))
+
+    def set_edges(self, edges):
+        self.edges = [int(e) for e in edges]
+        assert self.edges[0] == 0 and self.edges[-1] == self.H and all(a < b for a, b in zip(self.edges, self.edges[1:]))
+        self.ctx.set_band(self.edges[self.rank], self.edges[self.rank + 1])
+        self.barrier()
+
+    def render(self, rot: np.ndarray) -> int:
+        r0 = self.edges[self.rank]
+        self.ctx.render_into(rot, self.frame[r0 * self.W:])
+        self.k += 1
+        self.counters[self.rank] = self.k                   # the copy has completed (sloth_render synchronises)
+        return self.k
+
+    def wait(self, k: int) -> np.ndarray:
+        while int(self.counters.min()) < k:
+            pass
+        return self.frame
+
+    def rebalance(self, chunks_per_band) -> list[int]:
+        """New edges with equal shares of the work, from the chunks each band processed under the current edges
+        (work taken as uniform inside a band).  All ranks must call it with the same numbers."""
+        w = np.maximum(np.asarray(chunks_per_band, np.float64), 1.0)
+        cdf_rows = np.array(self.edges, np.float64)
+        cdf_work = np.concatenate([[0.0], np.cumsum(w)])
+        targets = cdf_work[-1] * np.arange(1, self.world) / self.world
+        cuts = np.interp(targets, cdf_work, cdf_rows)
+        edges = [0] + [int(round(c)) for c in cuts] + [self.H]
+        for i in range(1, len(edges)):                      # strictly increasing
+            edges[i] = max(edges[i], edges[i - 1] + 1)
+        edges[-1] = self.H
+        for i in range(len(edges) - 2, 0, -1):
+            edges[i] = min(edges[i], edges[i + 1] - 1)
+        self.set_edges(edges)
+        return edges
+
+    def close(self):
+        from . import host_unregister
+        self.barrier()
+        if self.page_lock:
+            host_unregister(self._whole)
+        del self.counters, self.frame, self._whole
+        self.shm.close()
+        self.barrier()
+        if self.rank == 0:
+            self.shm.unlink()

@@ -111,3 +111,41 @@ def test_webify_framing_matches_the_reference_player_data():
         # render.js only needs `frames` to be an array of strings: same JS shape on both sides
         assert re.fullmatch(r"let frames = \[\n(`\n[^`]*`,\n)*`\n[^`]*`\];\n", ours)
         assert re.fullmatch(r"let frames = \[\n(`\n[^`]*`,\n)*`\n[^`]*`\];\n", ref)
+
+
+def test_host_band_renderer_edges_and_shared_frame():
+    """multigpu.HostBandRenderer without a GPU: the shared-memory frame, the per-rank counters and the work-balanced
+    band edges (a stub context writes its band index into its rows)."""
+    import numpy as np
+    from rust_sloth_b200 import multigpu
+
+    class StubCtx:
+        def __init__(self, r): self.r, self.band = r, None
+        def resize(self, w, h): self.w, self.h = w, h
+        def set_band(self, a, b): self.band = (a, b)
+        def render_into(self, rot, out): out[:(self.band[1] - self.band[0]) * self.w] = 100 + self.r
+
+    W, H, world = 12, 40, 4
+    name = f"sloth_test_{os.getpid()}"
+    rs_ = [multigpu.HostBandRenderer(StubCtx(r), W, H, r, world, name, page_lock=False) for r in range(world)]
+    try:
+        assert rs_[0].edges == [0, 10, 20, 30, 40]
+        for r in rs_:
+            r.render(None)
+        frame = rs_[2].wait(1)
+        body = frame[:W * H].reshape(H, W)
+        assert all((body[10 * r:10 * r + 10] == 100 + r).all() for r in range(world))
+        assert (frame[W * H:] == ord(" ")).all()
+        # band 1 did 3x the work of the others: its rows shrink, edges stay strictly increasing and end at H
+        for r in rs_:
+            edges = r.rebalance([10, 30, 10, 10])
+        assert edges[0] == 0 and edges[-1] == H and all(a < b for a, b in zip(edges, edges[1:]))
+        assert edges[2] - edges[1] < 10 and edges == rs_[3].edges
+        for r in rs_:
+            r.render(None)
+        body = rs_[0].wait(2)[:W * H].reshape(H, W)
+        assert all((body[edges[r]:edges[r + 1]] == 100 + r).all() for r in range(world))
+    finally:
+        for r in reversed(rs_):
+            r.barrier = lambda: None
+            r.close()
