@@ -213,6 +213,9 @@ typedef struct sloth_stats {
     float xform_ms;            /* per-vertex transform kernel of the last sloth_render when timing is on (indexed path) */
     uint64_t l2_window_bytes;  /* bytes of transformed vertices kept L2-resident by an access-policy window (0 = none) */
     uint64_t l2_persist_max;   /* the device's persisting-L2 set-aside limit */
+    uint32_t tile_tris;        /* last frame: queued triangles rasterised by the binned tile path (the rest of walk_tris walked) */
+    uint32_t tile_pairs;       /* last frame: (tile, triangle) pairs */
+    uint32_t tiles_used;       /* last frame: non-empty screen tiles */
 } sloth_stats;
 
 SLOTH_API int sloth_stats_get(sloth_ctx *ctx, sloth_stats *out);

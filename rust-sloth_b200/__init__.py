@@ -75,6 +75,7 @@ class Stats(C.Structure):
         ("load_read_ms", C.c_float), ("load_parse_ms", C.c_float), ("load_commit_ms", C.c_float),
         ("n_vert", C.c_uint32), ("geom_path", C.c_uint32), ("xform_ms", C.c_float),
         ("l2_window_bytes", C.c_uint64), ("l2_persist_max", C.c_uint64),
+        ("tile_tris", C.c_uint32), ("tile_pairs", C.c_uint32), ("tiles_used", C.c_uint32),
     ]
 
     def as_dict(self) -> dict:

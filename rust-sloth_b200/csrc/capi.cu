@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "index.cuh"
 #include "tri_kernel.cuh"
+#include "tile_kernels.cuh"
 #include "flush.cuh"
 #include "loader.cuh"
 
@@ -130,6 +131,18 @@ struct sloth_ctx {
     uint32_t* walk_tri[2] = {nullptr, nullptr};      // k_geom3 -> k_tail queues, one per frame-state set
     unsigned long long* walk_base[2] = {nullptr, nullptr};
     uint32_t* irr_tri[2] = {nullptr, nullptr};
+    // binned tile path (tile_kernels.cuh): per frame-state set, one allocation for the tile arrays
+    unsigned long long* tile_info[2] = {nullptr, nullptr};   // [n_tri], with the walk queues
+    TileTri* tile_setup[2] = {nullptr, nullptr};             // [n_tri]
+    uint8_t* tile_region[2] = {nullptr, nullptr};            // TileAux | count[n_tiles+1] | cursor | (16-byte aligned) used | pairs
+    size_t tile_clear_bytes = 0;                             // aux + counters: cleared per frame
+    uint32_t tiles_x = 0, tiles_y = 0, pair_cap = 0;
+    // Off by default: parity-tested, but measured slower than the walk kernel on every bundled scene (config 3,
+    // "suzy suzy" at 4K: bin 6.5 + scan 15.6 + fill 12.0 + k_tile 44.7 + k_tail 6.7 = 86 us against 57 us for
+    // k_tail alone; profiles/README.md).  SLOTH_TILES=1 turns it on for frames of at least 512 x 256 cells,
+    // SLOTH_TILES=2 for frames of any size (tests).
+    bool tile_path = false;
+    bool tile_always = false;
     int last_set = 0;
     cudaStream_t resolve_stream = nullptr;
     cudaEvent_t ev_geom_done[2] = {nullptr, nullptr}, ev_resolved[2] = {nullptr, nullptr};
@@ -174,6 +187,9 @@ int free_frame_state(sloth_ctx* c)
     cudaFree(c->d_z);
     cudaFree(c->aux_region[0]);
     cudaFree(c->aux_region[1]);
+    cudaFree(c->tile_region[0]);
+    cudaFree(c->tile_region[1]);
+    c->tile_region[0] = c->tile_region[1] = nullptr;
     c->keys[0] = c->keys[1] = nullptr;
     c->d_cells[0] = c->d_cells[1] = nullptr;
     c->d_z = nullptr;
@@ -202,6 +218,16 @@ int alloc_frame_state(sloth_ctx* c)
     c->rowmax_bytes = ((((size_t)H + 31) & ~(size_t)31) + 64) * sizeof(uint32_t);
     c->aux_bytes = c->rowmax_bytes + sizeof(FrameAux);
     for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->aux_region[i], c->aux_bytes));
+    {   // tile path: only worth its four launches on frames with room for large triangles
+        c->tiles_x = (W + TILE_W - 1) / TILE_W;
+        c->tiles_y = (H + TILE_H - 1) / TILE_H;
+        const size_t n_tiles = (size_t)c->tiles_x * c->tiles_y;
+        c->pair_cap = (uint32_t)std::min<size_t>(4u << 20, std::max<size_t>(n_tiles * 32, 1u << 16));
+        c->tile_clear_bytes = sizeof(TileAux) + (n_tiles + 1) * sizeof(uint32_t);
+        const size_t head = (sizeof(TileAux) + (2 * n_tiles + 1) * sizeof(uint32_t) + 63) & ~(size_t)63;
+        const size_t bytes = head + n_tiles * sizeof(uint4) + (size_t)c->pair_cap * sizeof(TileTri);
+        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->tile_region[i], bytes));
+    }
     c->sized = true;
     return SLOTH_OK;
 }
@@ -310,6 +336,10 @@ int apply_carveout(sloth_ctx* c, int pct)
     CU(cudaFuncSetAttribute(k_resolve_odd, a, pct));
     CU(cudaFuncSetAttribute(k_clear_keys_odd, a, pct));
     CU(cudaFuncSetAttribute(k_xform, a, pct));
+    CU(cudaFuncSetAttribute(k_bin_count, a, pct));
+    CU(cudaFuncSetAttribute(k_bin_scan, a, pct));
+    CU(cudaFuncSetAttribute(k_bin_fill, a, pct));
+    CU(cudaFuncSetAttribute(k_tile, a, pct));
     CU(cudaFuncSetAttribute(k_tri<false, false, true>, a, pct));
     CU(cudaFuncSetAttribute(k_tri<false, true, true>, a, pct));
     CU(cudaFuncSetAttribute(k_tri<true, false, true>, a, pct));
@@ -415,14 +445,47 @@ int enqueue_geometry(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t s
     return SLOTH_OK;
 }
 
-// Follow-up pass of a frame (k_tail: queued row bands + irregular triangles) on stream `st`.
+TileState tile_state(const sloth_ctx* c, int set)
+{
+    const size_t n_tiles = (size_t)c->tiles_x * c->tiles_y;
+    uint8_t* base = c->tile_region[set];
+    TileState ts;
+    ts.aux = reinterpret_cast<TileAux*>(base);
+    ts.count = reinterpret_cast<uint32_t*>(base + sizeof(TileAux));
+    ts.cursor = ts.count + n_tiles + 1;
+    const size_t head = (sizeof(TileAux) + (2 * n_tiles + 1) * sizeof(uint32_t) + 63) & ~(size_t)63;
+    ts.used = reinterpret_cast<uint4*>(base + head);
+    ts.pairs = reinterpret_cast<TileTri*>(base + head + n_tiles * sizeof(uint4));
+    ts.info = c->tile_info[set];
+    ts.setup = c->tile_setup[set];
+    ts.tiles_x = c->tiles_x;
+    ts.tiles_y = c->tiles_y;
+    ts.pair_cap = c->pair_cap;
+    return ts;
+}
+
+// Follow-up pass of a frame on stream `st`: the triangles the geometry kernel queued (larger than 8 x 8 candidates)
+// are binned to screen tiles and rasterised per tile (k_bin_count / k_bin_scan / k_bin_fill / k_tile); what cannot be
+// binned (slivers whose rows do not provably end at the bounding box), and the non-finite triangles, go to k_tail.
+// Small frames skip the tile path: its four launches cost more than the few large triangles such a frame can hold.
 int enqueue_tail(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
 {
     if (!c->n_tri) return SLOTH_OK;
     const Scene sc = scene_of(c, set);
     const Queues q = make_queues(c, set);
+    const bool tiles = c->tile_path && (c->tile_always || (size_t)c->W * c->H >= (size_t)512 * 256);
+    if (tiles) {
+        const TileState ts = tile_state(c, set);
+        CU(cudaMemsetAsync(c->tile_region[set], 0, c->tile_clear_bytes, st));
+        const unsigned bin_blocks = (unsigned)c->sm_count * 4u;
+        k_bin_count<<<bin_blocks, 256, 0, st>>>(p, sc, q, ts);
+        k_bin_scan<<<1, 1024, 0, st>>>(ts);
+        k_bin_fill<<<bin_blocks, 256, 0, st>>>(q, ts);
+        k_tile<<<(unsigned)c->sm_count * 8u, TILE_W * TILE_H, 0, st>>>(p, sc, c->keys[set], q, ts);
+        c->launches += 4;
+    }
     const uint32_t wb = (uint32_t)c->sm_count * c->tail_blocks_per_sm, ib = std::max<uint32_t>(1u, (uint32_t)c->sm_count / 2u);
-    k_tail<<<wb + ib, 128, 0, st>>>(p, sc, c->keys[set], q, wb);
+    k_tail<<<wb + ib, 128, 0, st>>>(p, sc, c->keys[set], q, wb, tiles ? c->tile_info[set] : nullptr);
     c->launches += 1;
     return SLOTH_OK;
 }
@@ -732,8 +795,8 @@ int alloc_scene(sloth_ctx* c, size_t n_tri)
     c->sc_chunks = nullptr;
     c->sc_bounds = nullptr;
     for (int i = 0; i < 2; ++i) {
-        cudaFree(c->walk_tri[i]); cudaFree(c->walk_base[i]); cudaFree(c->irr_tri[i]);
-        c->walk_tri[i] = c->irr_tri[i] = nullptr; c->walk_base[i] = nullptr;
+        cudaFree(c->walk_tri[i]); cudaFree(c->walk_base[i]); cudaFree(c->irr_tri[i]); cudaFree(c->tile_info[i]); cudaFree(c->tile_setup[i]);
+        c->walk_tri[i] = c->irr_tri[i] = nullptr; c->walk_base[i] = nullptr; c->tile_info[i] = nullptr; c->tile_setup[i] = nullptr;
     }
     c->sc_a = c->sc_b = nullptr; c->sc_z3 = nullptr; c->sc_rgb = nullptr;
     c->have_scene = false;
@@ -750,6 +813,8 @@ int alloc_scene(sloth_ctx* c, size_t n_tri)
         CU(cudaMalloc(&c->walk_tri[i], n * sizeof(uint32_t)));
         CU(cudaMalloc(&c->walk_base[i], n * sizeof(unsigned long long)));
         CU(cudaMalloc(&c->irr_tri[i], n * sizeof(uint32_t)));
+        CU(cudaMalloc(&c->tile_info[i], n * sizeof(unsigned long long)));
+        CU(cudaMalloc(&c->tile_setup[i], n * sizeof(TileTri)));
     }
     return SLOTH_OK;
 }
@@ -814,6 +879,7 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     if (const char* g = std::getenv("SLOTH_GRID")) c->geom_blocks_per_sm = (uint32_t)std::max(1, std::atoi(g));
     if (const char* g = std::getenv("SLOTH_TGRID")) c->tri_blocks_per_sm = (uint32_t)std::min((int)T_BLOCKS_PER_SM, std::max(1, std::atoi(g)));
     if (const char* g = std::getenv("SLOTH_L2PERSIST")) c->l2_persist = std::atoi(g) != 0;
+    if (const char* g = std::getenv("SLOTH_TILES")) { c->tile_path = std::atoi(g) != 0; c->tile_always = std::atoi(g) == 2; }
     if (const char* g = std::getenv("SLOTH_PF")) c->pf_chunks = (uint32_t)std::min(64, std::max(0, std::atoi(g)));
     if (const char* g = std::getenv("SLOTH_PATH")) c->path_pref = std::min(2, std::max(0, std::atoi(g)));
     {
@@ -895,7 +961,7 @@ int sloth_ctx_destroy(sloth_ctx* c)
     cudaFree(c->sc_chunks);
     cudaFree(c->sc_bounds);
     free_index(c);
-    for (int i = 0; i < 2; ++i) { cudaFree(c->walk_tri[i]); cudaFree(c->walk_base[i]); cudaFree(c->irr_tri[i]); }
+    for (int i = 0; i < 2; ++i) { cudaFree(c->walk_tri[i]); cudaFree(c->walk_base[i]); cudaFree(c->irr_tri[i]); cudaFree(c->tile_info[i]); cudaFree(c->tile_setup[i]); }
     for (int i = 0; i < EV_N; ++i) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) {
         cudaEventDestroy(c->ev_rendered[i]);
@@ -1343,6 +1409,13 @@ int sloth_stats_get(sloth_ctx* c, sloth_stats* out)
         out->irregular_tris = aux.irr_count;
         out->stamp_fixups = aux.stamp_exact;
         out->chunks_processed = aux.chunks_done;
+        if (c->tile_region[c->last_set]) {
+            TileAux ta;
+            CU(cudaMemcpy(&ta, c->tile_region[c->last_set], sizeof ta, cudaMemcpyDeviceToHost));
+            out->tile_tris = ta.binned_tris;
+            out->tile_pairs = (uint32_t)std::min<unsigned long long>(ta.pairs_total, 0xFFFFFFFFull);
+            out->tiles_used = ta.n_tiles_used;
+        }
     }
     if (c->ev_valid) {
         if (c->last_was_batch && c->batch_pending) {

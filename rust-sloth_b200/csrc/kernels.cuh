@@ -489,7 +489,7 @@ __global__ void __maxnreg__(72) k_geom3(const __grid_constant__ FrameParams p, c
 // 2 x 16 / 4 x 8 for narrow triangles); a row ends when a lane of that row sees a
 // closing edge fail (everything right of it fails as well) or at the reference's maxx.
 SLOTH_DEV void walk_body(const FrameParams& p, const Scene& sc, unsigned long long* __restrict__ keys, const Queues& q,
-                         uint32_t n_blocks)
+                         uint32_t n_blocks, const unsigned long long* __restrict__ tile_info)
 {
     const unsigned long long packed = q.aux->walk_counter;
     const unsigned long long n_items = packed & ITEM_MASK;
@@ -506,6 +506,7 @@ SLOTH_DEV void walk_body(const FrameParams& p, const Scene& sc, unsigned long lo
             const uint32_t mid = (lo + hi) >> 1;
             if (q.walk_base[mid] <= item) lo = mid; else hi = mid;
         }
+        if (tile_info && tile_info[lo] != ~0ull) continue;   // rasterised by the tile path (tile_kernels.cuh)
         const uint32_t t = q.walk_tri[lo];
         const uint32_t band = (uint32_t)(item - q.walk_base[lo]);
         float v[9];
@@ -585,9 +586,9 @@ SLOTH_DEV void irregular_body(const FrameParams& p, const Scene& sc, unsigned lo
 // the remaining blocks take the irregular triangles.  Both queues are usually empty or tiny.
 __global__ void __launch_bounds__(128) k_tail(const __grid_constant__ FrameParams p, const Scene sc,
                                               unsigned long long* __restrict__ keys, const Queues q,
-                                              const uint32_t walk_blocks)
+                                              const uint32_t walk_blocks, const unsigned long long* __restrict__ tile_info)
 {
-    if (blockIdx.x < walk_blocks) walk_body(p, sc, keys, q, walk_blocks);
+    if (blockIdx.x < walk_blocks) walk_body(p, sc, keys, q, walk_blocks, tile_info);
     else irregular_body(p, sc, keys, q, blockIdx.x - walk_blocks, gridDim.x - walk_blocks);
 }
 

@@ -14,11 +14,14 @@ import scenes as S
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["soup", "indexed"])
+@pytest.fixture(params=["soup", "indexed", "indexed-tiles"])
 def geom_path(request, monkeypatch):
     """Runs the test once per geometry path: SLOTH_PATH pins what every context created inside the test uses
-    (1 = k_geom3 over the soup, 2 = k_xform + k_tri over the deduplicated vertices), whatever AUTO would pick."""
+    (1 = k_geom3 over the soup, 2 = k_xform + k_tri over the deduplicated vertices), whatever AUTO would pick;
+    "-tiles" additionally sends the queued large triangles through the binned tile path on frames of any size
+    (by default small frames leave them to the walk kernel)."""
     monkeypatch.setenv("SLOTH_PATH", "1" if request.param == "soup" else "2")
+    monkeypatch.setenv("SLOTH_TILES", "2" if request.param.endswith("tiles") else "0")
     return request.param
 
 
@@ -512,3 +515,30 @@ def test_indexed_scene_dedupes_by_bit_pattern_and_auto_picks_the_path():
         assert ctx.stats()["geom_path"] == rs.PATH_SOUP and ctx.stats()["n_vert"] == 0
     finally:
         ctx.close()
+
+
+def test_binned_tile_path_takes_the_large_triangles(monkeypatch):
+    """Config 3 ('suzy suzy' at 3840x2160, every fragment of the second copy an exact depth tie): the triangles the
+    geometry kernel queues are binned to 32 x 8 tiles and rasterised per tile (tile_kernels.cuh); the frame, the
+    z-buffer and the fragment count equal the oracle's, and equal the walk kernel's with the tile path off."""
+    xyz, rgb, s0 = S.soup("suzy_suzy")
+    rot = oracle.rotation(0.0, S.PI, 0.0)
+    ocells, oz, ocnt = oracle.render(xyz, rgb, s0, 3840, 2160, rot, mode=0)
+    monkeypatch.setenv("SLOTH_TILES", "1")     # the tile path is opt-in (measured slower than the walk kernel)
+    cells, z, st = gpu_frame(xyz, rgb, s0, 3840, 2160, rot)
+    assert st["walk_tris"] > 500 and st["tile_tris"] > 0.9 * st["walk_tris"] and st["tiles_used"] > 1000, st
+    assert_same(cells, z, ocells, oz, "suzy suzy 4K, tile path")
+    assert st["fragments"] == ocnt["covered"]
+    monkeypatch.setenv("SLOTH_TILES", "0")
+    cells0, z0, st0 = gpu_frame(xyz, rgb, s0, 3840, 2160, rot)
+    assert st0["tile_tris"] == 0 and np.array_equal(cells0, cells) and np.array_equal(z0, z)
+    monkeypatch.setenv("SLOTH_TILES", "1")
+    # wrap frame of the Pikachu turntable at a size where the tile path is on by default, odd width as well
+    xyz, rgb, s0 = S.soup("pikachu")
+    rot = oracle.rotation(0.0, oracle.turntable(0.0, 360)[144], 0.0)
+    for W, H in ((1280, 640), (1281, 641)):
+        ocells, oz, ocnt = oracle.render(xyz, rgb, s0, W, H, rot, mode=0)
+        cells, z, st = gpu_frame(xyz, rgb, s0, W, H, rot)
+        assert st["tile_tris"] > 0
+        assert_same(cells, z, ocells, oz, f"pikachu wrap frame {W}x{H}, tile path")
+        assert st["fragments"] == ocnt["covered"]
