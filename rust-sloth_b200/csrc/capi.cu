@@ -157,6 +157,7 @@ struct sloth_ctx {
     // device-side flush (text serialisation)
     char* d_text[2] = {nullptr, nullptr};
     size_t d_text_cap = 0;
+    size_t flush_blocks_cap = 0;     // entries of flush_block_sum / flush_block_off
     uint32_t* flush_block_sum = nullptr;
     unsigned long long* flush_block_off = nullptr;
     unsigned long long* d_text_total = nullptr;      // [2]
@@ -622,21 +623,28 @@ size_t text_bytes_per_cell(int mode) { return mode == 0 ? 1 : (mode == 1 ? 40 : 
 int ensure_text_buffers(sloth_ctx* c, int mode)
 {
     const size_t need = c->cells_per_frame * text_bytes_per_cell(mode) + 64;
+    const size_t nb = (c->cells_per_frame + FLUSH_CELLS_PER_BLOCK - 1) / FLUSH_CELLS_PER_BLOCK + 1;
     if (!c->h_text_total) {
         CU(cudaHostAlloc(&c->h_text_total, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
         CU(cudaMalloc(&c->d_text_total, 2 * sizeof(unsigned long long)));
         for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&c->ev_text[i], cudaEventDisableTiming));
     }
-    if (need > c->d_text_cap) {
+    // the text buffers grow with the bytes per frame, the per-block arrays with the CELLS per frame: a resize to
+    // more cells in a mode with fewer bytes per cell must still grow the latter (tracked separately)
+    if (need > c->d_text_cap || nb > c->flush_blocks_cap) {
         CU(cudaStreamSynchronize(c->resolve_stream));
         CU(cudaStreamSynchronize(c->copy_stream));
         for (int i = 0; i < 2; ++i) { cudaFree(c->d_text[i]); c->d_text[i] = nullptr; }
         cudaFree(c->flush_block_sum); cudaFree(c->flush_block_off);
-        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->d_text[i], need));
-        const size_t nb = (c->cells_per_frame + FLUSH_CELLS_PER_BLOCK - 1) / FLUSH_CELLS_PER_BLOCK + 1;
+        c->flush_block_sum = nullptr; c->flush_block_off = nullptr;
+        const size_t bytes = std::max(need, c->d_text_cap);
+        c->d_text_cap = 0;            // nothing counts as allocated until every cudaMalloc below has succeeded
+        c->flush_blocks_cap = 0;
+        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->d_text[i], bytes));
         CU(cudaMalloc(&c->flush_block_sum, nb * sizeof(uint32_t)));
         CU(cudaMalloc(&c->flush_block_off, nb * sizeof(unsigned long long)));
-        c->d_text_cap = need;
+        c->d_text_cap = bytes;
+        c->flush_blocks_cap = nb;
     }
     return SLOTH_OK;
 }

@@ -234,7 +234,8 @@ int loader_add_obj(sloth_ctx* c, DevBuf<unsigned char>& d_text, size_t len, cons
     CU(cudaMemcpyAsync(&out, d_out.p, sizeof out, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (out.err_parse != ~0ull) return ld_fail(out.err_parse);
-    if (mtl_failed) return fail(SLOTH_E_IO, "Expected to have materials. (%s)", mtl_err.c_str());   // inputs.rs:112
+    // inputs.rs:112; tobj 3.2.2 returns Ok(materials) whenever the final material list is non-empty
+    if (mtl_failed && n_mats == 0) return fail(SLOTH_E_IO, "Expected to have materials. (%s)", mtl_err.c_str());
     const size_t n_tri = out.tot.n_tris;
     if (n_tri > MAX_TRIS) return fail(SLOTH_E_TOO_LARGE, "%zu triangles; the depth key holds a 27-bit index (max %u)", n_tri, MAX_TRIS);
 
@@ -252,9 +253,8 @@ int loader_add_obj(sloth_ctx* c, DevBuf<unsigned char>& d_text, size_t len, cons
     CU(cudaMemcpyAsync(&out.err_export, &d_out.p->err_export, sizeof out.err_export, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (out.err_export != ~0ull) return ld_fail(out.err_export);
-    // tobj always pushes the model that is open at the end of the file, and to_meshes unwraps its material
-    if (n_mats && !(out.tot.final_mat & ld::MAT_FOUND))
-        return fail(SLOTH_E_PARSE, "%s (end of file)", ld_message(ld::LD_NO_MATERIAL));
+    // (material_id.unwrap() sits inside the reference's per-triangle loop, geometry.rs:109-110: k_obj_faces reports
+    // LD_NO_MATERIAL for every face that emits a triangle without a material; a trailing model without faces is fine)
     LoaderState::Segment seg;
     seg.xyz = d_xyz.release();
     seg.rgb = d_rgb.release();
@@ -266,11 +266,10 @@ int loader_add_obj(sloth_ctx* c, DevBuf<unsigned char>& d_text, size_t len, cons
 // STL bytes that are already on the device; `head` = the first min(len, 4096) bytes on the host
 int loader_add_stl(sloth_ctx* c, DevBuf<unsigned char>& d_text, size_t len, const unsigned char* head)
 {
-    // stl_io::create_stl_reader: ASCII when the stream starts with "solid" (after leading whitespace)
+    // stl_io::create_stl_reader: AsciiStlReader::probe decides (first line valid UTF-8 and starting with "solid ";
+    // host/mesh_io.cpp).  A first line longer than the 4 KB the host sees is judged on those 4 KB.
     const size_t head_len = std::min<size_t>(len, 4096);
-    size_t s = 0;
-    while (s < head_len && host_is_ws(head[s])) ++s;
-    const bool ascii = head_len - s >= 5 && std::memcmp(head + s, "solid", 5) == 0;
+    const bool ascii = sloth::stl_probe_ascii(head, head_len);
     DevBuf<float> d_xyz(c->stream);
     DevBuf<uint8_t> d_rgb(c->stream);
     size_t n_tri = 0;
@@ -296,6 +295,12 @@ int loader_add_stl(sloth_ctx* c, DevBuf<unsigned char>& d_text, size_t len, cons
         if (out.err_parse != ~0ull) return ld_fail(out.err_parse);
         if (out.tot.n_vertices % 3u) return fail(SLOTH_E_PARSE, "stl_io couldnt parse STL: truncated facet");
         n_tri = out.tot.n_vertices / 3u;
+        if (n_tri == 0 && len >= 84) {   // binary body behind a header that passes the probe (see host/mesh_io.cpp)
+            uint32_t n = 0;
+            std::memcpy(&n, head + 80, 4);
+            if (n != 0 && len == 84 + (size_t)n * 50)
+                return fail(SLOTH_E_PARSE, "stl_io couldnt parse STL: ASCII header (\"solid \") on a binary body");
+        }
         if (n_tri > MAX_TRIS) return fail(SLOTH_E_TOO_LARGE, "%zu triangles; the depth key holds a 27-bit index (max %u)", n_tri, MAX_TRIS);
         CU(d_xyz.alloc(n_tri * 9));
         ld::k_stl_ascii_vertices<<<line_blocks, 256, 0, c->stream>>>(d_text.p, d_line_start.p, n_lines, d_rec.p, d_pre.p, d_xyz.p);

@@ -140,15 +140,16 @@ bool export_model(const ObjState& st, const std::vector<Material>& mats, bool ha
     const size_t n_pos = st.pos.size() / 3;
     const bool has_vcol = !st.vcol.empty();
     uint8_t base[3] = {1, 1, 1};  // geometry.rs:91
-    if (!mats.empty()) {
-        if (!have_mat) {
+    if (!mats.empty() && have_mat)
+        for (int i = 0; i < 3; ++i) base[i] = f32_as_u8(mats[mat_id].diffuse[i] * 255.0f);
+    auto emit = [&](long a, long b, long c) -> bool {
+        // material_id.unwrap() sits inside the per-triangle loop (geometry.rs:109-110): a model without faces --
+        // the trailing one tobj always pushes, an `o name` with nothing after it -- never reaches it
+        if (!mats.empty() && !have_mat) {
             err = "model has no material although the material list is non-empty "
                   "(the reference panics on material_id.unwrap(), geometry.rs:110)";
             return false;
         }
-        for (int i = 0; i < 3; ++i) base[i] = f32_as_u8(mats[mat_id].diffuse[i] * 255.0f);
-    }
-    auto emit = [&](long a, long b, long c) -> bool {
         const long idx[3] = {a, b, c};
         for (int k = 0; k < 3; ++k) {
             if (idx[k] < 0 || (size_t)idx[k] >= n_pos) {
@@ -286,8 +287,9 @@ bool load_obj(const std::string& path, std::vector<SimpleMesh>& out, std::string
         }
     }
     flush_model();  // tobj always pushes the trailing model
-    if (mtl_failed) {
-        // inputs.rs:112: present.1.expect("Expected to have materials.")
+    if (mtl_failed && mats.empty()) {
+        // inputs.rs:112: present.1.expect("Expected to have materials.") -- tobj 3.2.2 returns Ok(materials) whenever the
+        // final material list is non-empty, whatever an earlier mtllib statement did
         err = "Expected to have materials. (" + mtl_err + ")";
         return false;
     }
@@ -304,6 +306,34 @@ bool load_obj(const std::string& path, std::vector<SimpleMesh>& out, std::string
         out.push_back(std::move(mesh));
     }
     return true;
+}
+
+bool stl_probe_ascii(const unsigned char* head, size_t n)
+{
+    size_t end = 0;
+    while (end < n && head[end] != '\n') ++end;
+    if (end < n) ++end;   // read_line includes the newline
+    // UTF-8 validation of the first line (BufRead::read_line fails on invalid UTF-8 and stl_io then reads binary)
+    for (size_t i = 0; i < end;) {
+        const unsigned char c = head[i];
+        size_t len = 0;
+        uint32_t cp = 0;
+        if (c < 0x80) { ++i; continue; }
+        else if ((c & 0xE0) == 0xC0) { len = 2; cp = c & 0x1Fu; }
+        else if ((c & 0xF0) == 0xE0) { len = 3; cp = c & 0x0Fu; }
+        else if ((c & 0xF8) == 0xF0) { len = 4; cp = c & 0x07u; }
+        else return false;
+        if (i + len > end) return false;
+        for (size_t k = 1; k < len; ++k) {
+            if ((head[i + k] & 0xC0) != 0x80) return false;
+            cp = (cp << 6) | (head[i + k] & 0x3Fu);
+        }
+        if ((len == 2 && cp < 0x80) || (len == 3 && cp < 0x800) || (len == 4 && cp < 0x10000) || cp > 0x10FFFF ||
+            (cp >= 0xD800 && cp <= 0xDFFF))
+            return false;
+        i += len;
+    }
+    return end >= 6 && std::memcmp(head, "solid ", 6) == 0;
 }
 
 bool load_stl(const std::string& path, std::vector<SimpleMesh>& out, std::string& err)
@@ -326,11 +356,8 @@ bool load_stl(const std::string& path, std::vector<SimpleMesh>& out, std::string
             mesh.bbox_max[d] = std::fmax(v[d], mesh.bbox_max[d]);
         }
     };
-    // stl_io::create_stl_reader: ASCII if the stream starts with "solid" (after
-    // leading whitespace), binary otherwise.
-    size_t s = 0;
-    while (s < data.size() && std::isspace((unsigned char)data[s])) ++s;
-    const bool ascii = data.compare(s, 5, "solid") == 0;
+    // stl_io::create_stl_reader: AsciiStlReader::probe decides (first line valid UTF-8 and starting with "solid ")
+    const bool ascii = stl_probe_ascii(reinterpret_cast<const unsigned char*>(data.data()), data.size());
     size_t n_tri = 0;
     if (ascii) {
         std::istringstream ss(data);
@@ -355,6 +382,16 @@ bool load_stl(const std::string& path, std::vector<SimpleMesh>& out, std::string
         if (nv != 0) {
             err = "stl_io couldnt parse STL: truncated facet";
             return false;
+        }
+        // A binary file whose 80-byte header happens to pass the probe: stl_io's ASCII reader then meets bytes
+        // that are no facet and fails; it must not load as an empty mesh (blank frame, infinite scale).
+        if (n_tri == 0 && data.size() >= 84) {
+            uint32_t n = 0;
+            std::memcpy(&n, data.data() + 80, 4);
+            if (n != 0 && data.size() == 84 + (size_t)n * 50) {
+                err = "stl_io couldnt parse STL: ASCII header (\"solid \") on a binary body";
+                return false;
+            }
         }
     } else {
         if (data.size() < 84) {

@@ -40,6 +40,12 @@ uint8_t f32_as_u8(float v);
 // ("filename: [..] couldn't load, ..").
 bool match_meshes(const std::string& arg, std::vector<SimpleMesh>& out, std::string& err);
 
+// stl_io 0.4.2's AsciiStlReader::probe (restated; the crate is not vendored): the stream is ASCII iff its first line
+// -- the bytes up to and including the first '\n', or all of them -- is valid UTF-8 and starts with "solid " (with
+// the space; no leading whitespace is skipped).  Everything else is read as binary.  `n` = bytes available in
+// `head` (the whole file or a prefix that contains the first line).
+bool stl_probe_ascii(const unsigned char* head, size_t n);
+
 bool load_obj(const std::string& path, std::vector<SimpleMesh>& out, std::string& err);
 bool load_stl(const std::string& path, std::vector<SimpleMesh>& out, std::string& err);
 

@@ -12,6 +12,7 @@
 // (inputs.rs:97); in image mode the rotation flags are taken from the sub-command only
 // (main.rs:43) and `-b` from the top level only (main.rs:34); `-h` is the height inside `image`.
 #include <poll.h>
+#include <signal.h>
 #include <sys/ioctl.h>
 #include <termios.h>
 #include <unistd.h>
@@ -65,6 +66,10 @@ int parse_level(int argc, char** argv, int i, bool sub, Matches& m)
         std::string a = argv[i];
         auto value = [&](const char* name) {
             if (i + 1 >= argc) usage_error(std::string("The argument '") + name + "' requires a value but none was supplied");
+            // clap 2 without allow_hyphen_values (inputs.rs sets none): a value that starts with '-' is taken for
+            // the next flag, so `-x -1.5` is an error there, too
+            if (argv[i + 1][0] == '-' && argv[i + 1][1] != '\0')
+                usage_error(std::string("Found argument '") + argv[i + 1] + "' which wasn't expected, or isn't valid in this context");
             return std::string(argv[++i]);
         };
         if (a == "-x" || a == "--yaw") m.values["x"] = value("--yaw <x>");
@@ -115,15 +120,29 @@ void check(int rc)
 }
 
 termios g_saved;
-bool g_raw = false;
+volatile sig_atomic_t g_raw = 0;
 void leave_raw()
 {
     if (g_raw) {
         std::fputs("\x1b[?25h", stdout);       // cursor::Show
         std::fflush(stdout);
         tcsetattr(STDIN_FILENO, TCSANOW, &g_saved);
-        g_raw = false;
+        g_raw = 0;
     }
+}
+
+// SIGTERM / SIGHUP / SIGINT (raw mode switches ISIG off, so these only arrive from outside): put the terminal back
+// before dying -- only async-signal-safe calls here.
+void on_fatal_signal(int sig)
+{
+    if (g_raw) {
+        const char show[] = "\x1b[?25h";
+        ssize_t ignored = write(STDOUT_FILENO, show, sizeof show - 1);
+        (void)ignored;
+        tcsetattr(STDIN_FILENO, TCSANOW, &g_saved);
+        g_raw = 0;
+    }
+    _exit(128 + sig);
 }
 
 bool terminal_size(uint32_t& w, uint32_t& h)   // crossterm::terminal::size()
@@ -189,8 +208,14 @@ int main(int argc, char** argv)
         }
         if (!match_turntable(sub, turntable, err)) { std::fprintf(stderr, "Error: %s\n", err.c_str()); return 1; }
         if (sub.values.count("frame count")) {
-            webify_todo = std::strtol(sub.values["frame count"].c_str(), &end, 10);
+            webify_todo = std::strtol(sub.values["frame count"].c_str(), &end, 10);   // i32 in the reference (main.rs:38-40)
             if (!end || *end) { std::fprintf(stderr, "Error: invalid digit found in string\n"); return 1; }
+            if (webify_todo < 0) {
+                // main.rs:57,92-99 with a negative count: the step is negative, the pitch never passes 9.42477 and
+                // `count - 1 == frame` never holds -- the reference prints frames forever.  Refuse instead.
+                std::fprintf(stderr, "Error: frame count %ld is negative (the reference would never stop exporting)\n", webify_todo);
+                return 1;
+            }
             webify = true;
         }
     }
@@ -247,8 +272,14 @@ int main(int argc, char** argv)
         termios raw = g_saved;
         cfmakeraw(&raw);
         tcsetattr(STDIN_FILENO, TCSANOW, &raw);
-        g_raw = true;
+        g_raw = 1;
         std::atexit(leave_raw);
+        struct sigaction sa;
+        std::memset(&sa, 0, sizeof sa);
+        sa.sa_handler = on_fatal_signal;
+        sigaction(SIGTERM, &sa, nullptr);
+        sigaction(SIGHUP, &sa, nullptr);
+        sigaction(SIGINT, &sa, nullptr);
     }
     std::fputs("\x1b[?25l", stdout);           // cursor::Hide
     const double target_frame_time = 1.0 / 500.0;   // fps_cap = 500
@@ -259,7 +290,9 @@ int main(int argc, char** argv)
         pollfd pfd{STDIN_FILENO, POLLIN, 0};
         if (poll(&pfd, 1, (int)(target_frame_time * 1000.0)) > 0) {
             char key = 0;
-            if (read(STDIN_FILENO, &key, 1) == 1 && (key == 'q' || key == 3)) break;   // 'q' or Ctrl-C
+            const ssize_t got = read(STDIN_FILENO, &key, 1);
+            if (got == 1 && (key == 'q' || key == 3)) break;   // 'q' or Ctrl-C
+            if (got <= 0) break;   // end of input / hang-up: nobody can press q any more (and poll would spin)
         }
         uint32_t tw = 0, th = 0;
         if (!terminal_size(tw, th)) { leave_raw(); std::fprintf(stderr, "Error: cannot get the terminal size\n"); return 1; }

@@ -336,3 +336,35 @@ def test_large_obj_matches_host_loader(tmp_path):
     path = write(tmp_path / "ico.obj", text)
     hx, hr, hs = assert_same_scene(path)
     assert np.array_equal(hx.view(np.uint32), xyz.view(np.uint32)) and hs == np.float32(xyz.max())
+
+
+def test_stl_flavour_probe_and_material_rules_on_the_device(tmp_path):
+    """The device loader decides ASCII / binary like stl_io's probe (first line valid UTF-8 and starting with "solid ")
+    and applies the reference's per-triangle material unwrap: the same crafted files as the host loader's tests."""
+    import test_host_loaders as H
+    ctx = rs.Context.blank(True)
+    try:
+        for k, (data, want) in enumerate(H.stl_probe_cases()):
+            path = tmp_path / f"p{k}.stl"
+            path.write_bytes(data)
+            if want is None:
+                with pytest.raises(rs.SlothError) as e:
+                    ctx.load_models(str(path))
+                assert "stl_io couldnt parse STL" in str(e.value), (k, str(e.value))
+            else:
+                n, _ = ctx.load_models(str(path))
+                assert n == want, k
+        (tmp_path / "m.mtl").write_text("newmtl red\nKd 1 0 0\n")
+        base = "mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nusemtl red\nf 1 2 3\n"
+        for tail in ("usemtl nosuch\n", "o empty\n"):
+            (tmp_path / "a.obj").write_text(base + tail)
+            n, _ = ctx.load_models(str(tmp_path / "a.obj"))
+            assert n == 1 and tuple(ctx.scene()[1][0]) == (255, 0, 0)
+        (tmp_path / "b.obj").write_text(base + "usemtl nosuch\nf 1 2 3\n")
+        with pytest.raises(rs.SlothError):
+            ctx.load_models(str(tmp_path / "b.obj"))
+        (tmp_path / "c.obj").write_text("mtllib missing.mtl\n" + base)
+        n, _ = ctx.load_models(str(tmp_path / "c.obj"))
+        assert n == 1
+    finally:
+        ctx.close()

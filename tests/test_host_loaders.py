@@ -176,3 +176,63 @@ def test_device_decimal_routine_grammar():
         if s == 0:
             assert np.float32(g).view(np.uint32) == np.float32(w).view(np.uint32), (t, g, w)
     assert np.signbit(got[1]) and np.signbit(got[8]) and got[23] == np.float32(3.4028235e38)
+
+
+def _binary_stl(header: bytes, tris) -> bytes:
+    body = b"".join(struct.pack("<12fH", 0, 0, 1, *t, 0) for t in tris)
+    return header.ljust(80, b"\0")[:80] + struct.pack("<I", len(tris)) + body
+
+
+STL_TRI = (0.0, 0.0, 0.0, 2.0, 0.0, 0.0, 0.0, 3.0, -1.0)
+
+
+def stl_probe_cases():
+    """(file bytes, expected triangles or None = the reference fails with 'stl_io couldnt parse STL').
+    stl_io 0.4.2 probes the FIRST LINE: ASCII iff it is valid UTF-8 and starts with "solid " (restated, unpinned)."""
+    return [
+        # binary, header starts with "solid" but the first line (up to the first 0x0A) is not valid UTF-8 -> binary reader
+        (_binary_stl(b"solid \xff\xfe made by some CAD tool", [STL_TRI]), 1),
+        # binary, header "solidworks ..." (no space after "solid") -> binary reader
+        (_binary_stl(b"solidworks export", [STL_TRI, STL_TRI]), 2),
+        # binary body behind a header that passes the probe (all bytes up to the first newline are ASCII): the
+        # reference's ASCII reader fails on it; it must not load as an empty mesh
+        (_binary_stl(b"solid ascii-looking header\n", [STL_TRI]), None),
+        # leading whitespace before "solid": not ASCII for stl_io -> binary reader -> too short -> error
+        (b"  solid x\n facet normal 0 0 1\n  outer loop\n   vertex 0 0 0\n   vertex 2 0 0\n   vertex 0 3 -1\n  endloop\n endfacet\nendsolid x\n", None),
+        # plain ASCII with zero facets: an empty mesh is what the reference gets, too
+        (b"solid empty\nendsolid empty\n", 0),
+    ]
+
+
+def test_stl_flavour_probe_follows_stl_io(tmp_path):
+    for k, (data, want) in enumerate(stl_probe_cases()):
+        path = tmp_path / f"p{k}.stl"
+        path.write_bytes(data)
+        if want is None:
+            with pytest.raises(rs.SlothError) as e:
+                rs.match_meshes(str(path))
+            assert "stl_io couldnt parse STL" in str(e.value), (k, str(e.value))
+        else:
+            (m,) = rs.match_meshes(str(path))
+            assert len(m) == want, k
+            if want:
+                assert np.array_equal(m.xyz[0], np.array(STL_TRI, np.float32))
+
+
+def test_material_unwrap_happens_per_triangle(tmp_path):
+    """geometry.rs:109-110: material_id.unwrap() sits inside the triangle loop -- a model without faces (the trailing
+    one tobj always pushes, `o name` with nothing after it, a final `usemtl <unknown>`) loads; a FACE without a known
+    material does not.  tobj returns Ok(materials) when the final list is non-empty, whatever an earlier mtllib did."""
+    write(tmp_path / "m.mtl", "newmtl red\nKd 1 0 0\n")
+    base = "mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nusemtl red\nf 1 2 3\n"
+    for tail in ("usemtl nosuch\n", "o empty\n", "usemtl nosuch\no also_empty\n"):
+        write(tmp_path / "a.obj", base + tail)
+        meshes = rs.match_meshes(str(tmp_path / "a.obj"))
+        assert sum(len(m) for m in meshes) == 1 and tuple(meshes[0].rgb[0]) == (255, 0, 0)
+    write(tmp_path / "b.obj", base + "usemtl nosuch\nf 1 2 3\n")
+    with pytest.raises(rs.SlothError) as e:
+        rs.match_meshes(str(tmp_path / "b.obj"))
+    assert "no material" in str(e.value)
+    write(tmp_path / "c.obj", "mtllib missing.mtl\n" + base)
+    meshes = rs.match_meshes(str(tmp_path / "c.obj"))
+    assert sum(len(m) for m in meshes) == 1
