@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "index.cuh"
 #include "tri_kernel.cuh"
+#include "tri2_kernel.cuh"
 #include "tile_kernels.cuh"
 #include "flush.cuh"
 #include "loader.cuh"
@@ -110,6 +111,7 @@ struct sloth_ctx {
     cudaEvent_t ev_xform[2] = {nullptr, nullptr};
     cudaEvent_t ev_batch_start = nullptr;
     uint32_t tri_blocks_per_sm = T_BLOCKS_PER_SM;   // SLOTH_TGRID overrides (profiling)
+    bool tri_pairs = true;            // k_tri2 (two chunks per warp turn) for whole-frame contexts; SLOTH_TRI2=0: k_tri
     uint32_t pf_chunks = 0;           // SLOTH_PF: L2 prefetch distance of k_tri's record stream (measured: hurts, off)
     size_t l2_persist_max = 0, l2_window_max = 0;   // device limits of the persisting-L2 set-aside / access window
     size_t l2_window_bytes = 0;       // bytes of (vxy, vz) currently covered by the persisting window
@@ -341,6 +343,10 @@ int apply_carveout(sloth_ctx* c, int pct)
     CU(cudaFuncSetAttribute(k_bin_scan, a, pct));
     CU(cudaFuncSetAttribute(k_bin_fill, a, pct));
     CU(cudaFuncSetAttribute(k_tile, a, pct));
+    CU(cudaFuncSetAttribute(k_tri2<false, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri2<true, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri2<false, false>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri2<true, false>, a, pct));
     CU(cudaFuncSetAttribute(k_tri<false, false, true>, a, pct));
     CU(cudaFuncSetAttribute(k_tri<false, true, true>, a, pct));
     CU(cudaFuncSetAttribute(k_tri<true, false, true>, a, pct));
@@ -372,9 +378,33 @@ int enqueue_geometry_indexed(sloth_ctx* c, const FrameParams& p, const Scene& sc
     // a clean scene under a bounded matrix cannot produce |x'|,|y'| > 2^40: skip the per-triangle test
     bool bounded = c->scene_clean;
     for (int i = 0; i < 8; ++i) bounded = bounded && std::fabs(p.m[i]) <= 131072.0f;
-    const bool rowmax_shared = c->rowmax_bytes <= 33024u;
-    const size_t dyn = (rowmax_shared ? c->rowmax_bytes : 0) + sizeof(TWarpSmem) * T_WARPS;
+    // the per-block copy of rowmax moves to shared memory while it does not cost a resident block (227 KB per SM,
+    // 1 KB reserved per block) -- or, for the tallest frames the 8-warp layout still takes, up to 33 KB
+    const size_t warp_smem = sizeof(TWarpSmem) * T_WARPS;
+    const bool rowmax_shared = c->rowmax_bytes <= 33024u && (T_WARPS <= 8 || (c->rowmax_bytes + warp_smem + 1024u) * bps <= 227u * 1024u);
+    const size_t dyn = (rowmax_shared ? c->rowmax_bytes : 0) + warp_smem;
     const bool band_mode = c->row1 != 0;
+    if (!band_mode && c->tri_pairs) {
+        // whole-frame contexts: two chunks per warp turn (tri2_kernel.cuh).  The per-block rowmax copy stays in shared
+        // memory only while it does not cost a resident block.
+        const uint32_t n_pairs = (n_chunks + 1) / 2;
+        const uint32_t grid2 = std::min<uint32_t>((n_pairs + T_WARPS - 1) / T_WARPS, (uint32_t)c->sm_count * bps);
+        const size_t warp_smem2 = sizeof(TWarpSmem2) * T_WARPS;
+        const bool shared2 = (c->rowmax_bytes + warp_smem2 + 1024u) * bps <= 228u * 1024u;
+        const size_t dyn2 = (shared2 ? c->rowmax_bytes : 0) + warp_smem2;
+        void (*kern2)(FrameParams, Scene, unsigned long long*, Queues) =
+            shared2 ? (bounded ? k_tri2<false, true> : k_tri2<true, true>) : (bounded ? k_tri2<false, false> : k_tri2<true, false>);
+        int pct = (int)(((dyn2 + 1024) * bps * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3;
+        pct = std::min(100, std::max(25, pct));
+        const int rc = apply_carveout(c, pct);
+        if (rc) return rc;
+        if (!xform_done) enqueue_xform(c, p, set, st);
+        if (kt) CU(cudaEventRecord(c->ev[EV_XFORM], st));
+        kern2<<<grid2, T_WARPS * 32, dyn2, st>>>(p, sc, c->keys[set], q);
+        c->launches += 1;
+        if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
+        return SLOTH_OK;
+    }
     void (*kern)(FrameParams, Scene, unsigned long long*, Queues);
     if (rowmax_shared)
         kern = bounded ? (band_mode ? k_tri<false, true, true> : k_tri<false, false, true>)
@@ -694,13 +724,14 @@ void free_index(sloth_ctx* c)
     c->pos_stride = 0;
 }
 
-// Room for n_vert unique vertices (+ the sentinel) and the records of n_tri triangles (padded to 32).
+// Room for n_vert unique vertices (+ the sentinel) and the records of n_tri triangles (padded to 64: k_tri2 takes
+// two chunks of 32 per turn).
 int alloc_index(sloth_ctx* c, size_t n_vert, size_t n_tri)
 {
     c->pos_stride = (n_vert + 1 + 63) & ~(size_t)63;
-    const size_t n_padded = (n_tri + 31) & ~(size_t)31;
+    const size_t n_padded = (n_tri + 63) & ~(size_t)63;
     CU(cudaMalloc(&c->sc_pos, 3 * c->pos_stride * sizeof(float)));
-    CU(cudaMalloc(&c->sc_rec, std::max<size_t>(n_padded, 32) * sizeof(uint4)));
+    CU(cudaMalloc(&c->sc_rec, std::max<size_t>(n_padded, 64) * sizeof(uint4)));
     // (x', y') and z' of every vertex in one allocation, so that one L2 access-policy window covers both
     const size_t n_slots = (n_vert + 1 + XFORM_PER_THREAD - 1) / XFORM_PER_THREAD * XFORM_PER_THREAD;   // k_xform writes whole groups
     const size_t xy_bytes = (n_slots * sizeof(float2) + 255) & ~(size_t)255;
@@ -779,7 +810,7 @@ int build_index(sloth_ctx* c, size_t n_tri)
         float* px = c->sc_pos;
         ix::k_ix_rank<<<n_blocks, 256, 0, c->stream>>>(sc, rep, (uint32_t)n_corners, block_sum, rank, px, px + c->pos_stride,
                                                       px + 2 * c->pos_stride);
-        const size_t n_padded = (n_tri + 31) & ~(size_t)31;
+        const size_t n_padded = (n_tri + 63) & ~(size_t)63;
         ix::k_ix_records<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(rep, rank, (uint32_t)n_tri, (uint32_t)n_padded, n_vert,
                                                                                   c->sc_rec);
         ix::k_ix_connectivity<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(c->sc_rec, (uint32_t)n_tri, (uint32_t)(n_padded / 32));
@@ -885,6 +916,7 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     if (const char* g = std::getenv("SLOTH_TAIL")) c->tail_blocks_per_sm = (uint32_t)std::max(1, std::atoi(g));
     if (const char* g = std::getenv("SLOTH_BATCH")) c->batch_max = (uint32_t)std::min(16, std::max(1, std::atoi(g)));
     if (const char* g = std::getenv("SLOTH_GRID")) c->geom_blocks_per_sm = (uint32_t)std::max(1, std::atoi(g));
+    if (const char* g = std::getenv("SLOTH_TRI2")) c->tri_pairs = std::atoi(g) != 0;
     if (const char* g = std::getenv("SLOTH_TGRID")) c->tri_blocks_per_sm = (uint32_t)std::min((int)T_BLOCKS_PER_SM, std::max(1, std::atoi(g)));
     if (const char* g = std::getenv("SLOTH_L2PERSIST")) c->l2_persist = std::atoi(g) != 0;
     if (const char* g = std::getenv("SLOTH_TILES")) { c->tile_path = std::atoi(g) != 0; c->tile_always = std::atoi(g) == 2; }
@@ -937,7 +969,8 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
         CU(cudaFuncSetAttribute(k_geom3<false, true, true>, a, lim));
         CU(cudaFuncSetAttribute(k_geom3<true, false, true>, a, lim));
         CU(cudaFuncSetAttribute(k_geom3<true, true, true>, a, lim));
-        const int tlim = 96 * 1024;   // k_tri: cp.async rings + fragment rings (45 KB) + up to 33 KB of row stamps
+        // k_tri: cp.async rings + fragment rings (6.4 KB per warp) + up to 33 KB of row stamps
+        const int tlim = (int)(sizeof(TWarpSmem) * T_WARPS) + 40 * 1024;
         CU(cudaFuncSetAttribute(k_tri<false, false, true>, a, tlim));
         CU(cudaFuncSetAttribute(k_tri<false, true, true>, a, tlim));
         CU(cudaFuncSetAttribute(k_tri<true, false, true>, a, tlim));
@@ -946,6 +979,11 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
         CU(cudaFuncSetAttribute(k_tri<false, true, false>, a, tlim));
         CU(cudaFuncSetAttribute(k_tri<true, false, false>, a, tlim));
         CU(cudaFuncSetAttribute(k_tri<true, true, false>, a, tlim));
+        const int tlim2 = (int)(sizeof(TWarpSmem2) * T_WARPS) + 40 * 1024;
+        CU(cudaFuncSetAttribute(k_tri2<false, true>, a, tlim2));
+        CU(cudaFuncSetAttribute(k_tri2<true, true>, a, tlim2));
+        CU(cudaFuncSetAttribute(k_tri2<false, false>, a, tlim2));
+        CU(cudaFuncSetAttribute(k_tri2<true, false>, a, tlim2));
     }
     *out = c;
     return SLOTH_OK;

@@ -28,7 +28,10 @@
 
 namespace sloth {
 
-static constexpr uint32_t T_WARPS = 8;     // warps per block
+#ifndef T_WARPS_PER_BLOCK
+#define T_WARPS_PER_BLOCK 8
+#endif
+static constexpr uint32_t T_WARPS = T_WARPS_PER_BLOCK;     // warps per block
 #ifndef T_BLOCKS_PER_SM
 #define T_BLOCKS_PER_SM 3      // persistent blocks per SM (shared memory: 3 x 60 KB)
 #endif

@@ -107,6 +107,8 @@ bool match_turntable(const Matches& m, float t[4], std::string& err)
         if (it != m.values.end() && !parse_f32(it->second, t[i])) { err = "invalid float literal"; return false; }
     }
     t[3] = 1.0f;                               // no speed flag exists: 1.0 rad/s
+    // test hook (tests/test_gpu_interactive.py): a standing turntable makes the interactive frames reproducible
+    if (const char* s = std::getenv("SLOTH_SPEED")) t[3] = std::strtof(s, nullptr);
     t[1] += 3.14159265358979323846f;           // "All models for some reason are backwards"
     return true;
 }
