@@ -276,6 +276,7 @@ def run_b200(args, rank, local_rank, world):
         ev1.record(stream)
         ctx.sync()
         launches_timed = ctx.stats()["kernel_launches"] - launches0   # kernels of this library, counted at launch
+        d_timed = d_cells[:cpf].clone()   # what the timed batch left behind (the load loop below overwrites d_cells)
         # keep the GPU in the same state a little longer so the 100 ms sampler sees the load (until it has
         # delivered a few samples: with 8 ranks starting nvidia-smi at once the first line can take a second)
         t_busy = time.time()
@@ -291,11 +292,11 @@ def run_b200(args, rank, local_rank, world):
     d_check = torch.empty(cpf + 2, dtype=torch.int32, device=f"cuda:{local_rank}")
     ctx.render_device(timed_rots[-1], d_check.data_ptr())
     ctx.sync()
-    same = bool(torch.equal(d_cells[:cpf], d_check[:cpf]))
+    same = bool(torch.equal(d_timed, d_check[:cpf]))
     post_check = {"last_timed_frame_equals_single_render": same,
-                  "cells_sha256": hashlib.sha256(d_cells[:cpf].cpu().numpy().tobytes()).hexdigest(),
+                  "cells_sha256": hashlib.sha256(d_timed.cpu().numpy().tobytes()).hexdigest(),
                   "frame": int(my_frames[-1])}
-    del d_check
+    del d_check, d_timed
 
     # ---- roofline: per-kernel events, one frame per sample --------------------------------
     ctx.stats_enable(kernel_timing=True)
@@ -325,21 +326,37 @@ def run_b200(args, rank, local_rank, world):
     del d2h_pin
 
     # ---- e2e: public API, host buffers ------------------------------------------------------
+    # Two passes over the same frames through sloth_render_batch: the plain wire (4-byte cells over PCIe) and the span
+    # wire (run lists over PCIe, the cells rebuilt by host threads inside the library); both leave the same bytes in
+    # the caller's buffer, which is checked on the last frame.
     ring = max(1, min(K, 64))   # page-locked frames (2.1 GB at 4K); a larger K reuses them, 64 frames per call
     pinned = rs.PinnedBuffer(ring * cpf)
     my_rots = np.stack([rots[f] for f in my_frames[Wm:]])
-    ctx.render_batch(my_rots[:min(K, 3)], pinned.array)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(0, K, ring):
-        ctx.render_batch(my_rots[i:i + ring], pinned.array)
-    e2e_s = time.perf_counter() - t0
-    barrier()
+    last_slot = (K - 1) % ring
 
-    times = torch.tensor([dev_ms, e2e_s * 1e3, d2h_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    def e2e_pass(wire):
+        ctx.set_wire(wire)
+        ctx.render_batch(my_rots[:min(K, 3)], pinned.array)
+        ctx.set_wire(wire)        # resets the wire statistics after the warm-up call
+        barrier()
+        t = time.perf_counter()
+        for i in range(0, K, ring):
+            ctx.render_batch(my_rots[i:i + ring], pinned.array)
+        dt = time.perf_counter() - t
+        barrier()
+        digest = hashlib.sha256(pinned.array[last_slot * cpf:(last_slot + 1) * cpf].tobytes()).hexdigest()
+        return dt, digest, ctx.wire_stats()
+
+    e2e_cells_s, cells_digest, _ = e2e_pass(rs.WIRE_CELLS)
+    e2e_s, spans_digest, wire_stats = e2e_pass(rs.WIRE_SPANS)
+    ctx.set_wire(rs.WIRE_CELLS)
+    post_check["e2e_last_frame_same_on_both_wires"] = cells_digest == spans_digest
+    post_check["e2e_last_frame_equals_device_frame"] = cells_digest == post_check["cells_sha256"]
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3, d2h_ms, e2e_cells_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max, d2h_ms_max = float(times[0]), float(times[1]), float(times[2])
+    dev_ms_max, e2e_ms_max, d2h_ms_max, e2e_cells_ms_max = float(times[0]), float(times[1]), float(times[2]), float(times[3])
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -359,6 +376,7 @@ def run_b200(args, rank, local_rank, world):
             traffic_src = f"{tj.get('capture', 'ncu --set full')} at commit {tj.get('commit', '?')}"
         fps = K * world / (dev_ms_max * 1e-3)
         e2e_fps = K * world / (e2e_ms_max * 1e-3)
+        e2e_cells_fps = K * world / (e2e_cells_ms_max * 1e-3)
         d2h_ceiling_fps = world / (d2h_ms_max * 1e-3)
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -367,11 +385,20 @@ def run_b200(args, rank, local_rank, world):
             "gfragments_per_s": frags_per_frame * fps / 1e9,
             "fragments_per_frame": frags_per_frame,
             "config": workload_config(n_tri, args.freq, world),
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": cpf * 4,
-                    "gfragments_per_s": frags_per_frame * e2e_fps / 1e9,
-                    # the end-to-end number has its own roofline: the measured device->host rate of the same bytes
-                    "d2h_gbs_measured": cpf * 4 * world / (d2h_ms_max * 1e-3) / 1e9,
-                    "d2h_ceiling_frames_per_s": d2h_ceiling_fps, "frac_of_d2h_ceiling": e2e_fps / d2h_ceiling_fps},
+            # headline: the span wire (SLOTH_WIRE_SPANS, one sloth_ctx_set_wire call); d2h bytes are what the library
+            # counted for rank 0's frames (run lists + their lengths, plain cells for frames without runs)
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 64,
+                    "d2h_bytes_per_step": wire_stats["d2h_bytes"] / max(wire_stats["frames"], 1),
+                    "wire": "spans (run lists over PCIe, 4-byte cells rebuilt into the caller's buffer by "
+                            f"{wire_stats['threads']} host threads per rank)",
+                    "frames_sent_as_plain_cells": wire_stats["plain_frames"],
+                    "host_bytes_written_per_step": cpf * 4,
+                    "gfragments_per_s": frags_per_frame * e2e_fps / 1e9},
+            # the same call over the plain wire, against its own roofline: the measured device->host rate of those bytes
+            "e2e_plain_cells": {"value": e2e_cells_fps, "unit": "frames/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": cpf * 4,
+                                "d2h_gbs_measured": cpf * 4 * world / (d2h_ms_max * 1e-3) / 1e9,
+                                "d2h_ceiling_frames_per_s": d2h_ceiling_fps,
+                                "frac_of_d2h_ceiling": e2e_cells_fps / d2h_ceiling_fps},
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,

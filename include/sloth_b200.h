@@ -126,6 +126,27 @@ SLOTH_API int sloth_render(sloth_ctx *ctx, const float rot[16], uint32_t *cells_
  * device->host copies are pipelined across frames. */
 SLOTH_API int sloth_render_batch(sloth_ctx *ctx, const float *rots, size_t n_frames, uint32_t *cells_out);
 
+/*
+ * What crosses PCIe when a frame's destination is host memory (Context.frame_buffer, context.rs:16-17).
+ *   SLOTH_WIRE_CELLS  the plain 4-byte cells (default): 33 MB per 3840x2160 frame, i.e. the PCIe rate of the box
+ *                     is the frame rate of sloth_render / sloth_render_batch.
+ *   SLOTH_WIRE_SPANS  run-length: the device sends one (start, cell) pair per run of equal cells -- the blank
+ *                     background and the doubled cells of rasterizer.rs:83-85 make frames mostly runs -- and a small
+ *                     pool of host threads inside the library rebuilds the 4-byte cells into cells_out while the
+ *                     next frames render (streaming stores).  Frames whose run list would exceed half the plain
+ *                     bytes are sent as plain cells.  cells_out receives the same bytes either way; z_out requests
+ *                     and the device-resident entry points are unaffected.  Threads: SLOTH_WIRE_THREADS, default =
+ *                     hardware threads / LOCAL_WORLD_SIZE (2..32).
+ * sloth_wire_stats: out[0] = frames sent since sloth_ctx_set_wire, out[1] = of those as plain cells, out[2] =
+ * device->host bytes they took, out[3] = pool threads.
+ * sloth_expand_spans: the host half on its own (no GPU involved): runs = n_runs pairs (start, cell), ascending
+ * starts, the first at 0; run i covers [start_i, start_{i+1}), the last one ends at n_cells.
+ */
+enum { SLOTH_WIRE_CELLS = 0, SLOTH_WIRE_SPANS = 1 };
+SLOTH_API int sloth_ctx_set_wire(sloth_ctx *ctx, int wire);
+SLOTH_API int sloth_wire_stats(const sloth_ctx *ctx, uint64_t out[4]);
+SLOTH_API int sloth_expand_spans(const uint32_t *runs, size_t n_runs, uint32_t *cells_out, size_t n_cells);
+
 /* Same frame, but the result stays on the device: d_cells is a 16-byte aligned device pointer
  * (same GPU) to W*H(+H) cells -- or band_rows*W cells when a band is set.
  * Runs on the context's stream; sloth_ctx_sync() waits for it. */

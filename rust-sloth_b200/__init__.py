@@ -41,6 +41,7 @@ HOST_LIB_PATH = os.path.join(_HERE, "libsloth_host.so")
 SLOTH_OK, SLOTH_E_ARG, SLOTH_E_CUDA, SLOTH_E_STATE, SLOTH_E_TOO_LARGE = 0, -1, -2, -3, -4
 SLOTH_E_IO, SLOTH_E_PARSE, SLOTH_E_UNSUPPORTED = -5, -6, -7
 PATH_AUTO, PATH_SOUP, PATH_INDEXED = 0, 1, 2   # sloth_ctx_set_path
+WIRE_CELLS, WIRE_SPANS = 0, 1                  # sloth_ctx_set_wire
 
 # every symbol include/sloth_b200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -55,6 +56,7 @@ ABI_SYMBOLS = [
     "sloth_scene_load", "sloth_loader_begin", "sloth_loader_add_obj", "sloth_loader_add_stl", "sloth_loader_commit",
     "sloth_scene_size", "sloth_scene_get",
     "sloth_device_alloc", "sloth_device_free", "sloth_ipc_export", "sloth_ipc_open", "sloth_ipc_close", "sloth_device_read", "sloth_device_write",
+    "sloth_ctx_set_wire", "sloth_wire_stats", "sloth_expand_spans",
 ]
 
 
@@ -146,6 +148,9 @@ def load_library() -> C.CDLL:
     L.sloth_ipc_close.argtypes = [C.c_int, vp]
     L.sloth_device_read.argtypes = [vp, vp, vp, C.c_size_t]
     L.sloth_device_write.argtypes = [vp, vp, vp, C.c_size_t]
+    L.sloth_ctx_set_wire.argtypes = [vp, C.c_int]
+    L.sloth_wire_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.sloth_expand_spans.argtypes = [C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t]
     _lib = L
     return L
 
@@ -379,6 +384,16 @@ class Context:
         """PATH_AUTO / PATH_SOUP / PATH_INDEXED for the scenes set from now on (sloth_ctx_set_path)."""
         _check(self._L.sloth_ctx_set_path(self._h, int(path)))
 
+    def set_wire(self, wire: int) -> None:
+        """WIRE_CELLS (plain 4-byte cells over PCIe) or WIRE_SPANS (run lists, cells rebuilt by host threads inside the
+        library) for render / render_batch from now on (sloth_ctx_set_wire); resets wire_stats()."""
+        _check(self._L.sloth_ctx_set_wire(self._h, int(wire)))
+
+    def wire_stats(self) -> dict:
+        out = (C.c_uint64 * 4)()
+        _check(self._L.sloth_wire_stats(self._h, out))
+        return {"frames": int(out[0]), "plain_frames": int(out[1]), "d2h_bytes": int(out[2]), "threads": int(out[3])}
+
     def close(self):
         if self._h:
             self._L.sloth_ctx_destroy(self._h)
@@ -610,6 +625,15 @@ def draw_mesh(context: Context, mesh: SimpleMesh, transform, shader=default_shad
     if shader is not default_shader:
         raise NotImplementedError("arbitrary closures cannot run on the device; use Context.set_shader(thresholds, glyphs)")
     context._draw(mesh, transform)
+
+
+def expand_spans(runs: np.ndarray, n_cells: int) -> np.ndarray:
+    """sloth_expand_spans: the host half of the span wire format on its own.  runs: (n, 2) uint32 rows (start, cell)."""
+    runs = np.ascontiguousarray(runs, np.uint32).reshape(-1, 2)
+    out = np.empty(int(n_cells), np.uint32)
+    _check(load_library().sloth_expand_spans(runs.ctypes.data_as(C.POINTER(C.c_uint32)), runs.shape[0],
+                                    out.ctypes.data_as(C.POINTER(C.c_uint32)), int(n_cells)))
+    return out
 
 
 def flush_bytes(cells: np.ndarray, color: bool, webify: bool, image: bool) -> bytes:

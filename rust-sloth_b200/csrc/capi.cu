@@ -10,7 +10,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -25,6 +29,8 @@
 #include "tri_kernel.cuh"
 #include "tri2_kernel.cuh"
 #include "tile_kernels.cuh"
+#include "spans.cuh"
+#include "../host/wire.hpp"
 #include "flush.cuh"
 #include "loader.cuh"
 
@@ -111,7 +117,9 @@ struct sloth_ctx {
     cudaEvent_t ev_xform[2] = {nullptr, nullptr};
     cudaEvent_t ev_batch_start = nullptr;
     uint32_t tri_blocks_per_sm = T_BLOCKS_PER_SM;   // SLOTH_TGRID overrides (profiling)
-    bool tri_pairs = true;            // k_tri2 (two chunks per warp turn) for whole-frame contexts; SLOTH_TRI2=0: k_tri
+    bool tri_pairs = false;           // SLOTH_TRI2=1: k_tri2 (two chunks per warp turn) for whole-frame contexts -- 5 % fewer
+                                      // instructions and 2 % faster alone, but its 80 registers x 768 threads leave no room for
+                                      // the neighbouring frames' k_xform / k_resolve blocks: 167 instead of 140 us per frame in batches
     uint32_t pf_chunks = 0;           // SLOTH_PF: L2 prefetch distance of k_tri's record stream (measured: hurts, off)
     size_t l2_persist_max = 0, l2_window_max = 0;   // device limits of the persisting-L2 set-aside / access window
     size_t l2_window_bytes = 0;       // bytes of (vxy, vz) currently covered by the persisting window
@@ -165,6 +173,17 @@ struct sloth_ctx {
     unsigned long long* d_text_total = nullptr;      // [2]
     unsigned long long* h_text_total = nullptr;      // [2], pinned
     cudaEvent_t ev_text[2] = {nullptr, nullptr};
+
+    // span wire format (spans.cuh, host/wire.hpp): sloth_ctx_set_wire(SLOTH_WIRE_SPANS)
+    int wire = 0;
+    static constexpr int WIRE_SLOTS = 6;             // page-locked staging slots (frames whose runs are in flight / being expanded)
+    uint2* d_runs[2] = {nullptr, nullptr};           // runs of the frame in cell buffer k&1
+    size_t runs_cap = 0;                             // runs per buffer and per staging slot (cells / 4: half the plain bytes)
+    uint2* h_runs[WIRE_SLOTS] = {};
+    cudaEvent_t ev_staged[WIRE_SLOTS] = {};
+    sloth::WirePool* wire_pool = nullptr;
+    struct WireSync* wire_sync = nullptr;            // free staging slots (shared with the pool's jobs)
+    uint64_t wire_d2h_bytes = 0, wire_frames = 0, wire_plain_frames = 0;   // since sloth_ctx_set_wire
 
     uint32_t stat_flags = 0;
     uint64_t frames = 0, launches = 0;
@@ -886,6 +905,164 @@ int finish_scene(sloth_ctx* c, size_t n_tri)
 
 extern "C" {
 
+// ---- span wire format: device side in spans.cuh, host side in host/wire.hpp -------------------------------------
+struct WireSync {   // shared by the thread that drives the GPU and the pool's expansion jobs
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int> free_slots;
+    int cuda_error = 0;   // first CUDA error an expansion job ran into
+};
+
+namespace {
+
+void free_wire_buffers(sloth_ctx* c)
+{
+    for (int i = 0; i < 2; ++i) { cudaFree(c->d_runs[i]); c->d_runs[i] = nullptr; }
+    for (int i = 0; i < sloth_ctx::WIRE_SLOTS; ++i) {
+        if (c->h_runs[i]) cudaFreeHost(c->h_runs[i]);
+        c->h_runs[i] = nullptr;
+    }
+    c->runs_cap = 0;
+}
+
+// Buffers of the span path for the current frame size: the run lists hold at most cells / 4 runs (half the bytes of
+// the plain cells) -- frames with more runs go out as plain cells.
+int ensure_wire_buffers(sloth_ctx* c)
+{
+    int rc = ensure_text_buffers(c, 0);   // block sums / offsets, the per-frame totals and their events
+    if (rc) return rc;
+    const size_t cap = std::max<size_t>(c->cells_per_frame / 4, 16);
+    if (!c->wire_pool) {
+        c->wire_pool = new sloth::WirePool(sloth::wire_default_threads());
+        c->wire_sync = new WireSync;
+        for (int i = 0; i < sloth_ctx::WIRE_SLOTS; ++i) CU(cudaEventCreateWithFlags(&c->ev_staged[i], cudaEventDisableTiming));
+    }
+    if (cap != c->runs_cap) {
+        CU(cudaStreamSynchronize(c->resolve_stream));
+        CU(cudaStreamSynchronize(c->copy_stream));
+        c->wire_pool->wait_idle();
+        free_wire_buffers(c);
+        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&c->d_runs[i], cap * sizeof(uint2)));
+        for (int i = 0; i < sloth_ctx::WIRE_SLOTS; ++i) CU(cudaHostAlloc(&c->h_runs[i], cap * sizeof(uint2), cudaHostAllocDefault));
+        c->runs_cap = cap;
+        std::lock_guard<std::mutex> lk(c->wire_sync->mu);
+        c->wire_sync->free_slots.clear();
+        for (int i = 0; i < sloth_ctx::WIRE_SLOTS; ++i) c->wire_sync->free_slots.push_back(i);
+    }
+    return SLOTH_OK;
+}
+
+// run list of the frame in `d_cells` -> d_runs, its length -> *d_total (all on `st`)
+int enqueue_spans(sloth_ctx* c, const uint32_t* d_cells, size_t n_cells, uint2* d_runs, unsigned long long* d_total, cudaStream_t st)
+{
+    const uint32_t nb = (uint32_t)((n_cells + FLUSH_CELLS_PER_BLOCK - 1) / FLUSH_CELLS_PER_BLOCK);
+    k_span_count<<<nb, FLUSH_THREADS, 0, st>>>(d_cells, (uint32_t)n_cells, c->flush_block_sum);
+    k_flush_scan<<<1, 1024, 0, st>>>(c->flush_block_sum, nb, c->flush_block_off, d_total);
+    k_span_write<<<nb, FLUSH_THREADS, 0, st>>>(d_cells, (uint32_t)n_cells, c->flush_block_off, d_total, (unsigned long long)c->runs_cap, d_runs);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    return SLOTH_OK;
+}
+
+// sloth_render_batch over the span wire format: per frame the device sends the run list (or, for a frame without
+// long runs, the plain cells); pool threads rebuild the caller's 4-byte cells while the next frames render.
+int render_batch_spans(sloth_ctx* c, const float* rots, size_t n_frames, uint32_t* cells_out)
+{
+    int rc = ensure_wire_buffers(c);
+    if (rc) return rc;
+    const size_t cpf = c->cells_per_frame;
+    WireSync* ws = c->wire_sync;
+    sloth::WirePool* pool = c->wire_pool;
+    const unsigned pieces = std::max(1u, std::min(pool->size(), 8u));
+    const int device = c->device;
+    // frame j's run list is complete on the device once ev_text[j&1] fires: read its length, start its copy, queue the expansion
+    auto finish = [&](size_t j) -> int {
+        const int b = (int)(j & 1);
+        CU(cudaEventSynchronize(c->ev_text[b]));
+        const size_t n_runs = (size_t)c->h_text_total[b];
+        uint32_t* dest = cells_out + j * cpf;
+        c->wire_frames += 1;
+        if (n_runs > c->runs_cap) {   // no runs worth sending: the plain cells
+            CU(cudaMemcpyAsync(dest, c->d_cells[b], cpf * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+            c->wire_plain_frames += 1;
+            c->wire_d2h_bytes += cpf * sizeof(uint32_t);
+            return SLOTH_OK;
+        }
+        int slot;
+        {
+            std::unique_lock<std::mutex> lk(ws->mu);
+            ws->cv.wait(lk, [&] { return !ws->free_slots.empty(); });
+            slot = ws->free_slots.back();
+            ws->free_slots.pop_back();
+        }
+        const sloth::Run* runs = reinterpret_cast<const sloth::Run*>(c->h_runs[slot]);
+        CU(cudaMemcpyAsync(c->h_runs[slot], c->d_runs[b], n_runs * sizeof(uint2), cudaMemcpyDeviceToHost, c->copy_stream));
+        CU(cudaEventRecord(c->ev_staged[slot], c->copy_stream));
+        CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+        c->wire_d2h_bytes += n_runs * sizeof(uint2) + sizeof(unsigned long long);
+        cudaEvent_t staged = c->ev_staged[slot];
+        auto left = std::make_shared<std::atomic<unsigned>>(pieces);
+        for (unsigned piece = 0; piece < pieces; ++piece) {
+            const size_t c0 = cpf * piece / pieces, c1 = cpf * (piece + 1) / pieces;
+            pool->submit([=] {
+                cudaSetDevice(device);
+                const cudaError_t e = cudaEventSynchronize(staged);
+                if (e == cudaSuccess) sloth::expand_runs(runs, n_runs, c0, c1, dest, cpf);
+                const bool last = left->fetch_sub(1) == 1;
+                if (last || e != cudaSuccess) {
+                    std::lock_guard<std::mutex> lk(ws->mu);
+                    if (e != cudaSuccess && !ws->cuda_error) ws->cuda_error = (int)e;
+                    if (last) ws->free_slots.push_back(slot);
+                }
+                if (last) ws->cv.notify_all();
+            });
+        }
+        return SLOTH_OK;
+    };
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    rc = enqueue_overlapped(
+        c, rots, n_frames,
+        [&](size_t k) -> int {   // cell and run buffers k&1 must have been copied out (frame k-2)
+            if (k >= 2) CU(cudaStreamWaitEvent(c->resolve_stream, c->ev_copied[k & 1], 0));
+            return SLOTH_OK;
+        },
+        [&](size_t k) { return c->d_cells[k & 1]; },
+        [&](size_t k) -> int {
+            const int b = (int)(k & 1);
+            int r = enqueue_spans(c, c->d_cells[b], cpf, c->d_runs[b], c->d_text_total + b, c->resolve_stream);
+            if (r) return r;
+            CU(cudaMemcpyAsync(c->h_text_total + b, c->d_text_total + b, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                               c->resolve_stream));
+            CU(cudaEventRecord(c->ev_text[b], c->resolve_stream));
+            return k >= 1 ? finish(k - 1) : SLOTH_OK;
+        });
+    if (!rc) rc = finish(n_frames - 1);
+    if (!rc) {
+        cudaError_t e = cudaEventRecord(c->ev[EV_END], c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->resolve_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->copy_stream);
+        if (e != cudaSuccess) rc = fail(SLOTH_E_CUDA, "span batch failed: %s", cudaGetErrorString(e));
+    }
+    pool->wait_idle();   // every frame of this call is in the caller's buffer (also on the error paths: jobs hold pointers into it)
+    if (rc) return rc;
+    if (ws->cuda_error) {
+        const int e = ws->cuda_error;
+        ws->cuda_error = 0;
+        return fail(SLOTH_E_CUDA, "span expansion failed: %s", cudaGetErrorString((cudaError_t)e));
+    }
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, c->ev[EV_START], c->ev[EV_END]));
+    c->batch_ms_per_frame = ms / (float)n_frames;
+    c->last_was_batch = true;
+    c->ev_valid = true;
+    c->ev_kernels_valid = false;
+    return SLOTH_OK;
+}
+
+}  // namespace
+
 const char* sloth_last_error(void) { return g_err; }
 
 int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
@@ -997,6 +1174,13 @@ int sloth_ctx_destroy(sloth_ctx* c)
     cudaStreamSynchronize(c->copy_stream);
     cudaStreamSynchronize(c->resolve_stream);
     free_frame_state(c);
+    if (c->wire_pool) {
+        c->wire_pool->wait_idle();
+        delete c->wire_pool;
+        delete c->wire_sync;
+        for (int i = 0; i < sloth_ctx::WIRE_SLOTS; ++i) if (c->ev_staged[i]) cudaEventDestroy(c->ev_staged[i]);
+    }
+    free_wire_buffers(c);
     for (int i = 0; i < 2; ++i) { cudaFree(c->d_text[i]); if (c->ev_text[i]) cudaEventDestroy(c->ev_text[i]); }
     cudaFree(c->flush_block_sum); cudaFree(c->flush_block_off); cudaFree(c->d_text_total);
     if (c->h_text_total) cudaFreeHost(c->h_text_total);
@@ -1160,6 +1344,11 @@ int sloth_render(sloth_ctx* c, const float rot[16], uint32_t* cells_out, float* 
     if (rc) return rc;
     if (!rot || !cells_out) return fail(SLOTH_E_ARG, "rot/cells_out is null");
     if (z_out && c->row1 != 0) return fail(SLOTH_E_ARG, "z_out is not available in band mode");
+    if (!z_out && c->wire == SLOTH_WIRE_SPANS) {   // one frame, its cells rebuilt by all pool threads
+        rc = render_batch_spans(c, rot, 1, cells_out);
+        c->last_was_batch = false;
+        return rc;
+    }
     if (z_out && !c->d_z) CU(cudaMalloc(&c->d_z, (size_t)c->W * c->H * sizeof(float)));
     rc = enqueue_frame(c, rot, c->d_cells[0], z_out ? c->d_z : nullptr, true);
     if (rc) return rc;
@@ -1262,12 +1451,43 @@ int sloth_ctx_sync(sloth_ctx* c)
     return SLOTH_OK;
 }
 
+
+int sloth_ctx_set_wire(sloth_ctx* c, int wire)
+{
+    if (!c) return fail(SLOTH_E_ARG, "null context");
+    if (wire != SLOTH_WIRE_CELLS && wire != SLOTH_WIRE_SPANS) return fail(SLOTH_E_ARG, "wire must be SLOTH_WIRE_CELLS or SLOTH_WIRE_SPANS");
+    c->wire = wire;
+    c->wire_d2h_bytes = c->wire_frames = c->wire_plain_frames = 0;
+    return SLOTH_OK;
+}
+
+int sloth_wire_stats(const sloth_ctx* c, uint64_t out[4])
+{
+    if (!c || !out) return fail(SLOTH_E_ARG, "null argument");
+    out[0] = c->wire_frames;
+    out[1] = c->wire_plain_frames;
+    out[2] = c->wire_d2h_bytes;
+    out[3] = c->wire_pool ? c->wire_pool->size() : 0;
+    return SLOTH_OK;
+}
+
+int sloth_expand_spans(const uint32_t* runs, size_t n_runs, uint32_t* cells_out, size_t n_cells)
+{
+    if ((!runs && n_runs) || (!cells_out && n_cells)) return fail(SLOTH_E_ARG, "null argument");
+    if (n_cells && (n_runs == 0 || runs[0] != 0)) return fail(SLOTH_E_ARG, "the first run must start at cell 0");
+    for (size_t i = 1; i < n_runs; ++i)
+        if (runs[2 * i] <= runs[2 * (i - 1)] || runs[2 * i] >= n_cells) return fail(SLOTH_E_ARG, "run %zu: starts must ascend inside the frame", i);
+    sloth::expand_runs(reinterpret_cast<const sloth::Run*>(runs), n_runs, 0, n_cells, cells_out, n_cells);
+    return SLOTH_OK;
+}
+
 int sloth_render_batch(sloth_ctx* c, const float* rots, size_t n_frames, uint32_t* cells_out)
 {
     int rc = check_ready(c);
     if (rc) return rc;
     if (n_frames == 0) return SLOTH_OK;
     if (!rots || !cells_out) return fail(SLOTH_E_ARG, "rots/cells_out is null");
+    if (c->wire == SLOTH_WIRE_SPANS) return render_batch_spans(c, rots, n_frames, cells_out);
     const size_t cpf = c->cells_per_frame;
     CU(cudaEventRecord(c->ev[EV_START], c->stream));
     rc = enqueue_overlapped(

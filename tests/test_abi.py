@@ -148,3 +148,22 @@ def test_cli_surface_follows_the_reference_clap_definition():
     assert r.returncode == 0 and r.stdout.startswith("Sloth 0.1") and "image -w <width> [-h <height>] [-j, --webify <frame count>]" in r.stdout
     r = run("-V")
     assert r.returncode == 0 and r.stdout.strip() == "Sloth 0.1"
+
+
+def test_span_expansion_on_the_host():
+    """sloth_expand_spans (the host half of SLOTH_WIRE_SPANS, no GPU involved): run lists against np.repeat, from
+    single-cell runs to runs long enough for the streaming-store path, at every alignment of the destination."""
+    rng = np.random.default_rng(11)
+    for n_cells, n_runs in [(1, 1), (7, 3), (1000, 1), (1000, 1000), (100_003, 37), (3840 * 64, 900), (1 << 20, 5)]:
+        starts = np.sort(rng.choice(np.arange(1, n_cells), size=min(n_runs, n_cells) - 1, replace=False)) if n_cells > 1 else np.array([], np.int64)
+        starts = np.concatenate([[0], starts]).astype(np.uint32)
+        vals = rng.integers(0, 1 << 32, size=starts.size, dtype=np.uint64).astype(np.uint32)
+        want = np.repeat(vals, np.diff(np.concatenate([starts, [n_cells]]).astype(np.int64)))
+        got = rs.expand_spans(np.stack([starts, vals], axis=1), n_cells)
+        assert np.array_equal(got, want), (n_cells, n_runs)
+    with pytest.raises(rs.SlothError):
+        rs.expand_spans(np.array([[1, 5]], np.uint32), 10)            # must start at cell 0
+    with pytest.raises(rs.SlothError):
+        rs.expand_spans(np.array([[0, 5], [4, 6], [4, 7]], np.uint32), 10)   # starts must ascend
+    with pytest.raises(rs.SlothError):
+        rs.expand_spans(np.array([[0, 5], [10, 6]], np.uint32), 10)   # inside the frame

@@ -14,7 +14,7 @@ import scenes as S
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["soup", "indexed", "indexed-tiles"])
+@pytest.fixture(params=["soup", "indexed", "indexed-tiles", "indexed-pairs"])
 def geom_path(request, monkeypatch):
     """Runs the test once per geometry path: SLOTH_PATH pins what every context created inside the test uses
     (1 = k_geom3 over the soup, 2 = k_xform + k_tri over the deduplicated vertices), whatever AUTO would pick;
@@ -22,6 +22,7 @@ def geom_path(request, monkeypatch):
     (by default small frames leave them to the walk kernel)."""
     monkeypatch.setenv("SLOTH_PATH", "1" if request.param == "soup" else "2")
     monkeypatch.setenv("SLOTH_TILES", "2" if request.param.endswith("tiles") else "0")
+    monkeypatch.setenv("SLOTH_TRI2", "1" if request.param.endswith("pairs") else "0")   # k_tri2: two chunks per warp turn
     return request.param
 
 
@@ -542,3 +543,42 @@ def test_binned_tile_path_takes_the_large_triangles(monkeypatch):
         assert st["tile_tris"] > 0
         assert_same(cells, z, ocells, oz, f"pikachu wrap frame {W}x{H}, tile path")
         assert st["fragments"] == ocnt["covered"]
+
+
+def test_span_wire_returns_the_same_cells():
+    """SLOTH_WIRE_SPANS (run lists over PCIe, cells rebuilt by host threads inside the library) hands back the same
+    buffers as the plain wire: single frames, batches (staging slots wrap), image and interactive mode, odd widths,
+    a resize in between, and a noise frame that has no runs (sent as plain cells)."""
+    rng = np.random.default_rng(5)
+    centre = (rng.random((60000, 1, 3), np.float32) * 1.9 - 0.95).astype(np.float32)   # confetti: runs of 2 cells
+    noise = (centre + (rng.random((60000, 3, 3), np.float32) * 0.05 - 0.025).astype(np.float32)).reshape(-1, 9)
+    noise_rgb = rng.integers(1, 255, size=(60000, 3)).astype(np.uint8)
+    cases = [("pikachu", *S.soup("pikachu"), True, 200, 100), ("skull", *S.soup("skull"), False, 321, 120),
+             ("icosphere", *meshes.icosphere(40), True, 640, 360), ("noise", noise, noise_rgb, np.float32(1.0), True, 300, 200)]
+    for name, xyz, rgb, s0, image, W, H in cases:
+        ctx = rs.Context.blank(image)
+        try:
+            ctx.set_scene(xyz, rgb, s0)
+            ctx.resize(W, H)
+            rots = np.stack([oracle.rotation(0.1 * k, S.PI + 0.37 * k, 0.05 * k) for k in range(17)])
+            plain = ctx.render_batch(rots).copy()
+            ctx.set_wire(rs.WIRE_SPANS)
+            spans = ctx.render_batch(rots)
+            assert np.array_equal(spans, plain), name
+            one, _ = ctx.render(rots[3])
+            assert np.array_equal(one, plain[3]), name
+            st = ctx.wire_stats()
+            assert st["frames"] == 18 and st["threads"] >= 1
+            plain_bytes = 18 * plain.shape[1] * 4
+            if name == "noise":
+                assert st["plain_frames"] > 0
+            else:
+                assert st["plain_frames"] == 0 and st["d2h_bytes"] < plain_bytes // 4, (name, st, plain_bytes)
+            ocells, _, _ = oracle.render(xyz, rgb, s0, W, H, rots[3], image=image, mode=0)
+            assert np.array_equal(one, ocells), name
+            ctx.resize(W // 2 + 1, H // 2)                      # other run-list capacity, odd / even flips
+            small = ctx.render_batch(rots[:5])
+            ctx.set_wire(rs.WIRE_CELLS)
+            assert np.array_equal(small, ctx.render_batch(rots[:5])), name
+        finally:
+            ctx.close()
