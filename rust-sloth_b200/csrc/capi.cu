@@ -115,7 +115,17 @@ struct sloth_ctx {
     float* vz[2] = {nullptr, nullptr};
     cudaStream_t xform_stream = nullptr;   // batches: k_xform of frame k+1 runs beside k_tri of frame k
     cudaEvent_t ev_xform[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stamped[2] = {nullptr, nullptr};   // k_super_stamp of the set's last frame has read its vxy
     cudaEvent_t ev_batch_start = nullptr;
+    // super-chunks (index.cuh): per-scene cone + unique-vertex list of every 256 triangles, per-frame list of the ones
+    // k_super_cert could not certify as back-facing
+    ix::SuperChunk* sc_super = nullptr;
+    uint32_t* sc_super_ids = nullptr;
+    uint32_t* live_sc[2] = {nullptr, nullptr};
+    uint32_t* skip_sc[2] = {nullptr, nullptr};
+    ConeCounts* cone_cnt[2] = {nullptr, nullptr};
+    uint32_t n_super = 0;             // full super-chunks of the resident scene
+    bool cone = true;                 // SLOTH_CONE=0: every chunk goes through k_tri
     uint32_t tri_blocks_per_sm = T_BLOCKS_PER_SM;   // SLOTH_TGRID overrides (profiling)
     bool tri_pairs = false;           // SLOTH_TRI2=1: k_tri2 (two chunks per warp turn) for whole-frame contexts -- 5 % fewer
                                       // instructions and 2 % faster alone, but its 80 registers x 768 threads leave no room for
@@ -302,6 +312,30 @@ void build_params(const sloth_ctx* c, const float rot[16], FrameParams& p)
         if (std::isfinite(k)) p.bf_k = std::nextafterf(k, std::numeric_limits<float>::infinity());
     }
     p.pf_chunks = c->pf_chunks;
+    // super-chunk certificate (k_super_cert): c = row0 x row1, |c|, the larger row norm and the coordinate error bound
+    // (four roundings of terms of magnitude <= |row|_1 * absmax + |translation|, with a factor 2 to spare)
+    p.cone_on = 0u;
+    p.cone_n_super = 0u;
+    p.cone_c[0] = p.cone_c[1] = p.cone_c[2] = p.cone_cnorm = p.cone_s = p.cone_ev = 0.0f;
+    if (c->scene_clean && c->cone && c->indexed && c->n_super && !band && std::isfinite(p.bf_k)) {
+        const double r0[3] = {p.m[0], p.m[1], p.m[2]}, r1[3] = {p.m[4], p.m[5], p.m[6]};
+        const double cx = r0[1] * r1[2] - r0[2] * r1[1], cy = r0[2] * r1[0] - r0[0] * r1[2], cz = r0[0] * r1[1] - r0[1] * r1[0];
+        const double cn = std::sqrt(cx * cx + cy * cy + cz * cz) * 1.000001;
+        const double s0 = std::sqrt(r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]), s1 = std::sqrt(r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
+        const double am = (double)c->scene_absmax;
+        const double xa = (std::fabs(r0[0]) + std::fabs(r0[1]) + std::fabs(r0[2])) * am + std::fabs((double)p.m[3]);
+        const double ya = (std::fabs(r1[0]) + std::fabs(r1[1]) + std::fabs(r1[2])) * am + std::fabs((double)p.m[7]);
+        const double ev = std::max(xa, ya) * std::ldexp(1.0, -24) * 8.0 + 1.0e-30;
+        const float f_cn = (float)cn, f_s = (float)(std::max(s0, s1) * 1.000001), f_ev = (float)(ev * 1.000001);
+        if (std::isfinite(f_cn) && std::isfinite(f_s) && std::isfinite(f_ev) && f_cn > 0.0f) {
+            p.cone_on = 1u;
+            p.cone_n_super = c->n_super;
+            p.cone_c[0] = (float)cx; p.cone_c[1] = (float)cy; p.cone_c[2] = (float)cz;
+            p.cone_cnorm = std::nextafterf(f_cn, std::numeric_limits<float>::infinity());
+            p.cone_s = std::nextafterf(f_s, std::numeric_limits<float>::infinity());
+            p.cone_ev = std::nextafterf(f_ev, std::numeric_limits<float>::infinity());
+        }
+    }
     p.cull_on = 0u;
     p.cull_scale = p.cull_pad = 0.0f;
     if (band && c->scene_clean && !(c->debug & 4u)) {
@@ -325,16 +359,34 @@ Queues make_queues(const sloth_ctx* c, int set)
     q.irr_tri = c->irr_tri[set];
     q.rowmax = reinterpret_cast<uint32_t*>(c->aux_region[set]);
     q.aux = reinterpret_cast<FrameAux*>(c->aux_region[set] + c->rowmax_bytes);
+    q.live_sc = c->live_sc[set];
+    q.skip_sc = c->skip_sc[set];
+    q.cone_cnt = c->cone_cnt[set];
     return q;
 }
 
 Scene scene_of(const sloth_ctx* c, int set)
 {
-    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb, c->sc_bounds, c->sc_rec, c->vxy[set], c->vz[set]};
+    Scene sc{c->sc_a, c->sc_b, c->sc_z3, c->sc_rgb, c->sc_bounds, c->sc_rec, c->vxy[set], c->vz[set], c->sc_super_ids};
     return sc;
 }
 
 // Triangle::mul once per unique vertex of the indexed scene, into frame-state set `set`, on stream `st`.
+// a clean scene under a bounded matrix cannot produce |x'|,|y'| > 2^40: no per-triangle regularity test needed
+bool bounded_frame(const sloth_ctx* c, const FrameParams& p)
+{
+    bool bounded = c->scene_clean;
+    for (int i = 0; i < 8; ++i) bounded = bounded && std::fabs(p.m[i]) <= 131072.0f;
+    return bounded;
+}
+
+// whole-frame, bounded: super-chunks certified back-facing for this frame's matrix are taken off k_tri's list
+bool cone_frame(const sloth_ctx* c, const FrameParams& p) { return c->row1 == 0 && !c->tri_pairs && p.cone_on && bounded_frame(c, p); }
+
+// Everything of the indexed path that can run ahead of k_tri, into frame-state set `set` on stream `st`: Triangle::mul
+// once per unique vertex (k_xform) and, for cone frames, the super-chunk certificate (two lists and their lengths,
+// which live apart from the per-frame aux region: that one still belongs to the resolve of two frames ago when, in
+// batches, this runs on the transform stream one frame ahead of the triangle kernel).
 int enqueue_xform(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
 {
     const float* px = c->sc_pos;
@@ -342,6 +394,11 @@ int enqueue_xform(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
     k_xform<<<(n_threads + 255) / 256, 256, 0, st>>>(p, px, px + c->pos_stride, px + 2 * c->pos_stride, c->n_vert, c->vxy[set],
                                                      c->vz[set]);
     c->launches += 1;
+    if (cone_frame(c, p)) {
+        CU(cudaMemsetAsync(c->cone_cnt[set], 0, sizeof(ConeCounts), st));
+        k_super_cert<<<(c->n_super + 255) / 256, 256, 0, st>>>(p, c->sc_super, c->n_super, make_queues(c, set));
+        c->launches += 1;
+    }
     return SLOTH_OK;
 }
 
@@ -362,6 +419,10 @@ int apply_carveout(sloth_ctx* c, int pct)
     CU(cudaFuncSetAttribute(k_bin_scan, a, pct));
     CU(cudaFuncSetAttribute(k_bin_fill, a, pct));
     CU(cudaFuncSetAttribute(k_tile, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<false, false, true, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_tri<false, false, false, true>, a, pct));
+    CU(cudaFuncSetAttribute(k_super_cert, a, pct));
+    CU(cudaFuncSetAttribute(k_super_stamp, a, pct));
     CU(cudaFuncSetAttribute(k_tri2<false, true>, a, pct));
     CU(cudaFuncSetAttribute(k_tri2<true, true>, a, pct));
     CU(cudaFuncSetAttribute(k_tri2<false, false>, a, pct));
@@ -394,9 +455,7 @@ int enqueue_geometry_indexed(sloth_ctx* c, const FrameParams& p, const Scene& sc
     const uint32_t n_chunks = (c->n_tri + 31) / 32;
     const uint32_t bps = c->tri_blocks_per_sm;
     const uint32_t grid = std::min<uint32_t>((n_chunks + T_WARPS - 1) / T_WARPS, (uint32_t)c->sm_count * bps);
-    // a clean scene under a bounded matrix cannot produce |x'|,|y'| > 2^40: skip the per-triangle test
-    bool bounded = c->scene_clean;
-    for (int i = 0; i < 8; ++i) bounded = bounded && std::fabs(p.m[i]) <= 131072.0f;
+    const bool bounded = bounded_frame(c, p);
     // the per-block copy of rowmax moves to shared memory while it does not cost a resident block (227 KB per SM,
     // 1 KB reserved per block) -- or, for the tallest frames the 8-warp layout still takes, up to 33 KB
     const size_t warp_smem = sizeof(TWarpSmem) * T_WARPS;
@@ -420,6 +479,19 @@ int enqueue_geometry_indexed(sloth_ctx* c, const FrameParams& p, const Scene& sc
         if (!xform_done) enqueue_xform(c, p, set, st);
         if (kt) CU(cudaEventRecord(c->ev[EV_XFORM], st));
         kern2<<<grid2, T_WARPS * 32, dyn2, st>>>(p, sc, c->keys[set], q);
+        c->launches += 1;
+        if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
+        return SLOTH_OK;
+    }
+    if (cone_frame(c, p)) {
+        // k_super_cert (enqueue_xform) has split the super-chunks into the certified ones (k_super_stamp adds their row
+        // stamps before the resolve) and the rest, whose chunks k_tri<CONE> works through
+        const int rc = apply_carveout(c, std::min(100, std::max(25, (int)(((dyn + 1024) * bps * 100 + 228 * 1024 - 1) / (228 * 1024)) + 3)));
+        if (rc) return rc;
+        if (!xform_done) enqueue_xform(c, p, set, st);
+        if (kt) CU(cudaEventRecord(c->ev[EV_XFORM], st));
+        if (rowmax_shared) k_tri<false, false, true, true><<<grid, T_WARPS * 32, dyn, st>>>(p, sc, c->keys[set], q);
+        else k_tri<false, false, false, true><<<grid, T_WARPS * 32, dyn, st>>>(p, sc, c->keys[set], q);
         c->launches += 1;
         if (kt) CU(cudaEventRecord(c->ev[EV_GEOM], st));
         return SLOTH_OK;
@@ -523,6 +595,13 @@ int enqueue_tail(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
     if (!c->n_tri) return SLOTH_OK;
     const Scene sc = scene_of(c, set);
     const Queues q = make_queues(c, set);
+    if (c->indexed && cone_frame(c, p) && p.image && !(p.debug & 2u)) {
+        // row stamps of the super-chunks k_super_cert took off k_tri's list (reads this set's transformed vertices:
+        // the transform of the frame after next waits for ev_stamped)
+        k_super_stamp<<<(c->n_super + 7) / 8, 256, 0, st>>>(p, c->sc_super_ids, c->vxy[set], q);
+        c->launches += 1;
+        CU(cudaEventRecord(c->ev_stamped[set], st));
+    }
     const bool tiles = c->tile_path && (c->tile_always || (size_t)c->W * c->H >= (size_t)512 * 256);
     if (tiles) {
         const TileState ts = tile_state(c, set);
@@ -617,8 +696,12 @@ int enqueue_overlapped(sloth_ctx* c, const float* rots, size_t n_frames, BeforeF
         build_params(c, rots + 16 * k, p);
         const bool split = c->indexed && c->n_tri;
         if (split) {   // k_xform(k) on its own stream: it runs beside k_tri(k-1), as soon as k_tri(k-2) has let go of the set
-            if (k >= 2) CU(cudaStreamWaitEvent(c->xform_stream, c->ev_geom_done[set], 0));
-            else CU(cudaStreamWaitEvent(c->xform_stream, c->ev_batch_start, 0));
+            if (k >= 2) {
+                CU(cudaStreamWaitEvent(c->xform_stream, c->ev_geom_done[set], 0));
+                CU(cudaStreamWaitEvent(c->xform_stream, c->ev_stamped[set], 0));   // no-op unless a cone frame used the set
+            } else {
+                CU(cudaStreamWaitEvent(c->xform_stream, c->ev_batch_start, 0));
+            }
             if (tr) mark(c->xform_stream);
             if (!(c->debug & 64u) || k < 2) enqueue_xform(c, p, set, c->xform_stream);   // bit 6: timing experiment (wrong frames)
             if (tr) mark(c->xform_stream);
@@ -728,6 +811,10 @@ int check_ready(sloth_ctx* c)
 void free_index(sloth_ctx* c)
 {
     cudaFree(c->sc_pos); cudaFree(c->sc_rec); cudaFree(c->vxy[0]);   // both sets of (vxy, vz) live in one allocation
+    cudaFree(c->sc_super); cudaFree(c->sc_super_ids); cudaFree(c->live_sc[0]); cudaFree(c->live_sc[1]); cudaFree(c->skip_sc[0]); cudaFree(c->skip_sc[1]); cudaFree(c->cone_cnt[0]); cudaFree(c->cone_cnt[1]);
+    c->sc_super = nullptr; c->sc_super_ids = nullptr; c->live_sc[0] = c->live_sc[1] = c->skip_sc[0] = c->skip_sc[1] = nullptr;
+    c->cone_cnt[0] = c->cone_cnt[1] = nullptr;
+    c->n_super = 0;
     c->sc_pos = nullptr; c->sc_rec = nullptr;
     c->vxy[0] = c->vxy[1] = nullptr; c->vz[0] = c->vz[1] = nullptr;
     if (c->l2_window_bytes) {   // drop the residency window of the transformed vertices
@@ -834,6 +921,17 @@ int build_index(sloth_ctx* c, size_t n_tri)
                                                                                   c->sc_rec);
         ix::k_ix_connectivity<<<(unsigned)((n_padded + 255) / 256), 256, 0, c->stream>>>(c->sc_rec, (uint32_t)n_tri, (uint32_t)(n_padded / 32));
         c->launches += 3;
+        c->n_super = (uint32_t)(n_tri / ix::SC_TRIS);
+        if (c->n_super) {
+            CU_IX(cudaMalloc(&c->sc_super, (size_t)c->n_super * sizeof(ix::SuperChunk)));
+            CU_IX(cudaMalloc(&c->sc_super_ids, (size_t)c->n_super * ix::SC_IDS * sizeof(uint32_t)));
+            for (int i = 0; i < 2; ++i) CU_IX(cudaMalloc(&c->live_sc[i], (size_t)c->n_super * sizeof(uint32_t)));
+            for (int i = 0; i < 2; ++i) CU_IX(cudaMalloc(&c->skip_sc[i], (size_t)c->n_super * sizeof(uint32_t)));
+            for (int i = 0; i < 2; ++i) CU_IX(cudaMalloc(&c->cone_cnt[i], sizeof(ConeCounts)));
+            ix::k_ix_super<<<c->n_super, 256, 0, c->stream>>>(c->sc_rec, px, px + c->pos_stride, px + 2 * c->pos_stride, c->sc_super,
+                                                              c->sc_super_ids);
+            c->launches += 1;
+        }
         CU_IX(cudaGetLastError());
         CU_IX(cudaStreamSynchronize(c->stream));
         c->indexed = true;
@@ -1094,6 +1192,7 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     if (const char* g = std::getenv("SLOTH_BATCH")) c->batch_max = (uint32_t)std::min(16, std::max(1, std::atoi(g)));
     if (const char* g = std::getenv("SLOTH_GRID")) c->geom_blocks_per_sm = (uint32_t)std::max(1, std::atoi(g));
     if (const char* g = std::getenv("SLOTH_TRI2")) c->tri_pairs = std::atoi(g) != 0;
+    if (const char* g = std::getenv("SLOTH_CONE")) c->cone = std::atoi(g) != 0;
     if (const char* g = std::getenv("SLOTH_TGRID")) c->tri_blocks_per_sm = (uint32_t)std::min((int)T_BLOCKS_PER_SM, std::max(1, std::atoi(g)));
     if (const char* g = std::getenv("SLOTH_L2PERSIST")) c->l2_persist = std::atoi(g) != 0;
     if (const char* g = std::getenv("SLOTH_TILES")) { c->tile_path = std::atoi(g) != 0; c->tile_always = std::atoi(g) == 2; }
@@ -1124,6 +1223,7 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
     }
     CU(cudaEventCreateWithFlags(&c->ev_batch_start, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&c->ev_xform[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) CU(cudaEventCreateWithFlags(&c->ev_stamped[i], cudaEventDisableTiming));
     for (int i = 0; i < EV_N; ++i) CU(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) {
         CU(cudaEventCreateWithFlags(&c->ev_rendered[i], cudaEventDisableTiming));
@@ -1156,6 +1256,8 @@ int sloth_ctx_create(int device, int image_mode, sloth_ctx** out)
         CU(cudaFuncSetAttribute(k_tri<false, true, false>, a, tlim));
         CU(cudaFuncSetAttribute(k_tri<true, false, false>, a, tlim));
         CU(cudaFuncSetAttribute(k_tri<true, true, false>, a, tlim));
+        CU(cudaFuncSetAttribute(k_tri<false, false, true, true>, a, tlim));
+        CU(cudaFuncSetAttribute(k_tri<false, false, false, true>, a, tlim));
         const int tlim2 = (int)(sizeof(TWarpSmem2) * T_WARPS) + 40 * 1024;
         CU(cudaFuncSetAttribute(k_tri2<false, true>, a, tlim2));
         CU(cudaFuncSetAttribute(k_tri2<true, true>, a, tlim2));
@@ -1209,6 +1311,7 @@ int sloth_ctx_destroy(sloth_ctx* c)
     if (c->xform_stream) cudaStreamDestroy(c->xform_stream);
     if (c->ev_batch_start) cudaEventDestroy(c->ev_batch_start);
     for (int i = 0; i < 2; ++i) if (c->ev_xform[i]) cudaEventDestroy(c->ev_xform[i]);
+    for (int i = 0; i < 2; ++i) if (c->ev_stamped[i]) cudaEventDestroy(c->ev_stamped[i]);
     delete c;
     return SLOTH_OK;
 }

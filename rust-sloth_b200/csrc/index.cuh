@@ -233,6 +233,149 @@ __global__ void __launch_bounds__(256) k_ix_connectivity(uint4* __restrict__ rec
     rec[t] = r;
 }
 
+// ---------------------------------------------------------------------------------
+// Super-chunks: 8 consecutive chunks = 256 triangles.  Per super-chunk, once per scene:
+//   * the cone of its triangles' object-space normals n_t = (V1-V3) x (V2-V1) (axis, half-angle), the smallest |n_t|
+//     and the longest edge -- the rotation-independent half of the certificate "every triangle of this super-chunk
+//     is back-facing by a margin" that k_super_pass (tri_kernel.cuh) completes per frame;
+//   * the list of its unique vertex ids (at most SC_IDS), from which the row range the super-chunk stamps is read
+//     off without touching its triangles.
+// A super-chunk is certifiable only when it is full, every triangle has a non-zero normal, the cone is narrower than
+// 60 degrees, it has at most SC_IDS unique vertices, and every triangle but the first shares a vertex with an earlier
+// one (then the row ranges of its triangles form one interval, see k_ix_connectivity).  One block per super-chunk.
+// ---------------------------------------------------------------------------------
+static constexpr uint32_t SC_CHUNKS = 8;
+static constexpr uint32_t SC_TRIS = SC_CHUNKS * 32u;
+static constexpr uint32_t SC_IDS = 384;          // 12 per lane of the warp that reads them
+
+struct SuperChunk {        // 32 bytes
+    float ax, ay, az;      // unit cone axis times cos(half-angle)      (half-angle rounded up)
+    float sin_theta;       // sin(half-angle), rounded up; 2 = not certifiable
+    float inv_nmin;        // 1 / min |n_t|, rounded up
+    float emax;            // longest edge of any triangle, rounded up
+    uint32_t n_ids, pad;
+};
+
+__device__ __forceinline__ double block_reduce(double v, int op, double* s_part)   // op 0 sum, 1 min, 2 max; 256 threads
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const double o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        v = op == 0 ? v + o : (op == 1 ? fmin(v, o) : fmax(v, o));
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31u) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = s_part[0];
+    for (int w = 1; w < 8; ++w) r = op == 0 ? r + s_part[w] : (op == 1 ? fmin(r, s_part[w]) : fmax(r, s_part[w]));
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_ix_super(const uint4* __restrict__ rec, const float* __restrict__ px,
+                                                  const float* __restrict__ py, const float* __restrict__ pz,
+                                                  SuperChunk* __restrict__ out, uint32_t* __restrict__ ids)
+{
+    __shared__ unsigned long long s_key[1024];
+    __shared__ double s_part[8];
+    __shared__ uint32_t s_warp[8];
+    __shared__ int s_fail;
+    const uint32_t sc = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint4 r = rec[(size_t)sc * SC_TRIS + tid];
+    const uint32_t id[3] = {r.x, r.y, r.z};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) s_key[tid * 3u + j] = ((unsigned long long)id[j] << 32) | tid;
+    s_key[768u + tid] = ~0ull;
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+    for (uint32_t k = 2; k <= 1024u; k <<= 1)      // bitonic sort of (vertex id, triangle) pairs
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = tid; i < 1024u; i += 256u) {
+                const uint32_t x = i ^ j;
+                if (x > i) {
+                    const unsigned long long a = s_key[i], b = s_key[x];
+                    if ((a > b) == ((i & k) == 0u)) { s_key[i] = b; s_key[x] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // unique ids in ascending order: position i starts a new id
+    uint32_t first[3], mine = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const uint32_t i = tid * 3u + j;
+        first[j] = (i == 0u || (uint32_t)(s_key[i] >> 32) != (uint32_t)(s_key[i - 1u] >> 32)) ? 1u : 0u;
+        mine += first[j];
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t off = incl - mine, n_ids = 0;
+    for (uint32_t w = 0; w < 8u; ++w) {
+        if (w < warp) off += s_warp[w];
+        n_ids += s_warp[w];
+    }
+    uint32_t* my_ids = ids + (size_t)sc * SC_IDS;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        if (first[j]) {
+            if (off < SC_IDS) my_ids[off] = (uint32_t)(s_key[tid * 3u + j] >> 32);
+            ++off;
+        }
+    const uint32_t id0 = (uint32_t)(s_key[0] >> 32);
+    for (uint32_t i = n_ids + tid; i < SC_IDS; i += 256u) my_ids[i] = id0;   // padding: a vertex that is in the list anyway
+    // every triangle but the first shares a vertex with an earlier one (smallest triangle index per id = the low
+    // word of the id's first sorted pair)
+    bool linked = tid == 0u;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        uint32_t lo = 0, hi = 768u;
+        const unsigned long long want = (unsigned long long)id[j] << 32;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_key[mid] < want) lo = mid + 1u; else hi = mid;
+        }
+        if ((uint32_t)s_key[lo] < tid) linked = true;
+    }
+    // normal cone, in double
+    const double x1 = px[id[0]], y1 = py[id[0]], z1 = pz[id[0]];
+    const double x2 = px[id[1]], y2 = py[id[1]], z2 = pz[id[1]];
+    const double x3 = px[id[2]], y3 = py[id[2]], z3 = pz[id[2]];
+    const double ax = x1 - x3, ay = y1 - y3, az = z1 - z3, bx = x2 - x1, by = y2 - y1, bz = z2 - z1;
+    const double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+    const double len = sqrt(nx * nx + ny * ny + nz * nz);
+    const double e3x = x3 - x2, e3y = y3 - y2, e3z = z3 - z2;
+    const double emax_t = sqrt(fmax(fmax(ax * ax + ay * ay + az * az, bx * bx + by * by + bz * bz), e3x * e3x + e3y * e3y + e3z * e3z));
+    const bool good = linked && len > 0.0 && isfinite(len) && isfinite(emax_t);
+    if (!good) s_fail = 1;   // benign race: every writer stores 1
+    const double ux = good ? nx / len : 0.0, uy = good ? ny / len : 0.0, uz = good ? nz / len : 0.0;
+    double sx = block_reduce(ux, 0, s_part), sy = block_reduce(uy, 0, s_part), sz = block_reduce(uz, 0, s_part);
+    const double sl = sqrt(sx * sx + sy * sy + sz * sz);
+    if (sl > 0.0) { sx /= sl; sy /= sl; sz /= sl; }
+    const double cmin = block_reduce(good ? ux * sx + uy * sy + uz * sz : -1.0, 1, s_part);
+    const double nmin = block_reduce(good ? len : 0.0, 1, s_part);
+    const double emax = block_reduce(good ? emax_t : 0.0, 2, s_part);
+    __syncthreads();
+    if (tid == 0) {
+        SuperChunk o;
+        const double cs = cmin - 1.0e-6;   // cosine of the half-angle, rounded down
+        const bool ok = !s_fail && sl > 0.0 && n_ids <= SC_IDS && cs >= 0.5 && nmin > 0.0;
+        const double sn = ok ? sqrt(fmax(0.0, 1.0 - cs * cs)) + 1.0e-6 : 2.0;
+        o.ax = (float)(sx * cs); o.ay = (float)(sy * cs); o.az = (float)(sz * cs);
+        o.sin_theta = ok ? __double2float_ru(sn) : 2.0f;
+        o.inv_nmin = ok ? __double2float_ru(1.000001 / nmin) : 0.0f;
+        o.emax = ok ? __double2float_ru(emax * 1.000001) : 0.0f;
+        o.n_ids = n_ids;
+        o.pad = 0u;
+        if (!isfinite(o.inv_nmin) || !isfinite(o.emax)) o.sin_theta = 2.0f;
+        out[sc] = o;
+    }
+}
+
 // sloth_scene_set_indexed: positions[indices[..]] (geometry.rs:99-107) -> the resident soup streams and colours;
 // ids are checked against n_vert (*bad counts the triangles that fail, they become all-zero triangles).
 __global__ void __launch_bounds__(256) k_ix_expand_input(const float* __restrict__ pos, uint32_t n_vert, const uint32_t* __restrict__ idx,

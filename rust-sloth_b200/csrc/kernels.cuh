@@ -28,6 +28,12 @@ struct FrameAux {
     uint32_t pad[9];
 };
 
+// Lengths of the two super-chunk lists of a frame (k_super_cert); cleared on the transform stream, apart from FrameAux.
+struct ConeCounts {
+    uint32_t n_live;   // entries of Queues::live_sc: super-chunks left for k_tri
+    uint32_t n_skip;   // entries of Queues::skip_sc: certified back-facing, only their row stamps remain
+};
+
 struct Queues {
     uint32_t* __restrict__ walk_tri;             // [n_tri]
     unsigned long long* __restrict__ walk_base;  // [n_tri] first item id of that triangle (ascending)
@@ -36,6 +42,9 @@ struct Queues {
     // '\n' marker (rasterizer.rs:89-91), 0 = row never stamped.  [H + 64]
     uint32_t* __restrict__ rowmax;
     FrameAux* __restrict__ aux;
+    uint32_t* __restrict__ live_sc;              // [super-chunks] the ones k_super_cert could not certify as back-facing
+    uint32_t* __restrict__ skip_sc;              // [super-chunks] the certified ones: only their row stamps remain
+    ConeCounts* __restrict__ cone_cnt;
 };
 
 // ---------------------------------------------------------------------------------

@@ -25,6 +25,7 @@
 // round-to-nearest operations in the same order as raster_core.cuh's soup path.
 #pragma once
 #include "kernels.cuh"
+#include "index.cuh"
 
 namespace sloth {
 
@@ -115,12 +116,104 @@ SLOTH_DEV void t_emit(const FrameParams& p, const Scene& sc, const TRing& wq, ui
     emit_fragment(p, s, sh, tri, x, y, w0, w1, w2, keys);
 }
 
+// ---------------------------------------------------------------------------------
+// k_super_cert: once per frame, before k_tri (bounded whole-frame scenes of the indexed path), over the
+// super-chunks of 256 triangles (index.cuh).  It completes the back-face certificate for this frame's matrix;
+// a certified super-chunk never reaches k_tri -- k_super_stamp, which runs between k_tri and the resolve of the frame,
+// stamps the rows its triangles would have stamped; the others are appended to the list k_tri works through.
+//
+// Certificate.  The doubled screen area k_tri computes for a triangle is, in exact arithmetic on the ideal
+// coordinates, A = c . n_t with c = (row 0 of M) x (row 1 of M) and n_t = (V1-V3) x (V2-V1).  All unit normals of the
+// super-chunk lie within theta of the axis a, so with beta = angle(c, a):  A <= |n_t| |c| cos(beta - theta) <=
+// n_min (c.a cos(theta) + |c| sin(theta))  as soon as that bound is negative.  k_tri proves a triangle back-facing
+// when its COMPUTED area is below -T, T = (larger bbox side) * bf_k (backface_proven).  With e = bound on the
+// rounding error of a computed coordinate, L = emax * cone_s + 2e >= every bbox side, eta = 2e + 2^-23 L >= the error
+// of a computed edge difference:  |computed area - A| <= 4 L eta + 2 eta^2 + 2^-21 (L + eta)^2 =: E  and  T <= L bf_k.
+// The super-chunk is skipped when  n_min (c.a cos(theta) + |c| sin(theta)) <= -2 (L bf_k + E)  (twice what is needed,
+// plus 1e-5 |c| for the float evaluation of this very inequality): then every one of its triangles would have been
+// proven back-facing by k_tri, none has a candidate, and all it contributes are row stamps.
+//
+// Stamps.  The triangles hang together through shared vertices, so together they stamp exactly the rows
+// [ceil(max(min y', 1)), ceil(min(max y', H-1))) over the super-chunk's vertices (ceil commutes with min / max); y'
+// comes from k_xform's output.  The value stamped is the index of the super-chunk's LAST chunk (+1): rowmax is only
+// ever compared with the chunk of a fragment's triangle (stamp_beats_fragment), fragments never come from a skipped
+// super-chunk, and every index inside the super-chunk compares alike with every index outside it.
+// ---------------------------------------------------------------------------------
+// k_super_cert: lane = super-chunk.  Certified ones go to the skip list (k_super_stamp), the others to the list k_tri
+// works through; one warp-aggregated reservation per list and warp (the order of the lists carries no meaning).
+__global__ void __launch_bounds__(256) k_super_cert(const __grid_constant__ FrameParams p, const ix::SuperChunk* __restrict__ super,
+                                                    uint32_t n_sc, const Queues q)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t sc = blockIdx.x * 256u + threadIdx.x;
+    bool skip = false;
+    if (sc < n_sc) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(super + sc));        // ax ay az sin_theta
+        const float4 b = __ldg(reinterpret_cast<const float4*>(super + sc) + 1);    // inv_nmin emax n_ids pad
+        const float e = p.cone_ev;
+        const float L = b.y * p.cone_s + 2.0f * e;
+        const float eta = 2.0f * e + 1.1920929e-07f * L;
+        const float E = 4.0f * L * eta + 2.0f * eta * eta + 4.7683716e-07f * (L + eta) * (L + eta);
+        const float Tm = L * p.bf_k;
+        const float K = 2.002f * (Tm + E);
+        const float lhs = p.cone_c[0] * a.x + p.cone_c[1] * a.y + p.cone_c[2] * a.z + 1.00001f * p.cone_cnorm * a.w +
+                          1.00001f * K * b.x + 1.0e-5f * p.cone_cnorm;
+        skip = a.w < 1.5f && Tm > 1.0e-20f && lhs <= 0.0f;   // NaN / inf anywhere: not skipped
+    }
+    const unsigned m_skip = __ballot_sync(0xFFFFFFFFu, skip);
+    const unsigned m_live = __ballot_sync(0xFFFFFFFFu, sc < n_sc && !skip);
+    uint32_t base_live = 0, base_skip = 0;
+    if (lane == 0) {
+        if (m_live) base_live = atomicAdd(&q.cone_cnt->n_live, (uint32_t)__popc(m_live));
+        if (m_skip) base_skip = atomicAdd(&q.cone_cnt->n_skip, (uint32_t)__popc(m_skip));
+    }
+    base_live = __shfl_sync(0xFFFFFFFFu, base_live, 0);
+    base_skip = __shfl_sync(0xFFFFFFFFu, base_skip, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (skip) q.skip_sc[base_skip + __popc(m_skip & below)] = sc;
+    else if (sc < n_sc) q.live_sc[base_live + __popc(m_live & below)] = sc;
+}
+
+// Row range [lo, hi) a certified super-chunk stamps (image mode), by one warp: min / max of y' over its vertex list.
+SLOTH_DEV void super_rows(const FrameParams& p, const uint32_t* __restrict__ ids, const float2* __restrict__ vxy, uint32_t sc,
+                          uint32_t lane, uint32_t& lo, uint32_t& hi)
+{
+    const uint32_t* my = ids + (size_t)sc * ix::SC_IDS;
+    float y[ix::SC_IDS / 32];
+#pragma unroll
+    for (uint32_t j = 0; j < ix::SC_IDS / 32; ++j) y[j] = __ldg(&vxy[__ldg(my + j * 32u + lane)].y);
+    float mn = y[0], mx = y[0];
+#pragma unroll
+    for (uint32_t j = 1; j < ix::SC_IDS / 32; ++j) { mn = fminf(mn, y[j]); mx = fmaxf(mx, y[j]); }
+    lo = __reduce_min_sync(0xFFFFFFFFu, __float2uint_rz(ceilf(fmaxf(mn, 1.0f))));
+    hi = __reduce_max_sync(0xFFFFFFFFu, __float2uint_rz(ceilf(fminf(mx, p.hm1))));
+}
+
+// k_super_stamp (image mode, after k_tri, before the resolve of the same frame): one warp per entry of the skip list,
+// taken from the end -- the list is roughly ascending, so the highest indices reach a row first and most later
+// entries find it stamped already (one load instead of an atomic on a contended word).
+__global__ void __launch_bounds__(256) k_super_stamp(const __grid_constant__ FrameParams p, const uint32_t* __restrict__ ids,
+                                                     const float2* __restrict__ vxy, const Queues q)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t i = blockIdx.x * 8u + (threadIdx.x >> 5), n_skip = q.cone_cnt->n_skip;
+    if (i >= n_skip) return;
+    const uint32_t s_c = q.skip_sc[n_skip - 1u - i];
+    uint32_t lo, hi;
+    super_rows(p, ids, vxy, s_c, lane, lo, hi);
+    const uint32_t value = s_c * ix::SC_CHUNKS + ix::SC_CHUNKS;   // 1 + index of its last chunk
+    for (uint32_t r = lo + lane; r < hi; r += 32u)
+        if (__ldcg(q.rowmax + r) < value) atomicMax(q.rowmax + r, value);
+}
+
 // Dynamic shared memory of one block: [rowmax copy (ROWMAX_SHARED)] [TWarpSmem x T_WARPS]
 SLOTH_DEV size_t t_rowmax_words(uint32_t H) { return ((H + 31u) & ~31u) + 64u; }
 
 // ROWMAX_SHARED: the per-block copy of rowmax lives in dynamic shared memory (frames up to ~8 K rows), so the row
 // stamps are shared-memory atomics (ATOMS) instead of generic ones.
-template <bool CHECK_REGULAR, bool BAND, bool ROWMAX_SHARED>
+// CONE: the chunks come from the list of super-chunks k_super_pass left over (whole-frame, bounded scenes), followed by
+// the chunks behind the last full super-chunk.
+template <bool CHECK_REGULAR, bool BAND, bool ROWMAX_SHARED, bool CONE = false>
 __global__ void __launch_bounds__(T_WARPS * 32, T_REG_BLOCKS)
 k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long* __restrict__ keys, const Queues q)
 {
@@ -159,7 +252,11 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     // of k + 2 and k + 4 are one XOR away.  Band contexts keep `live`, a shift register over the next five
     // iterations (bit j <-> iteration k + j: not culled): only live chunks are copied, gathered and computed.
     // Past the end the record copies are clamped to the warp's last chunk (valid memory, results unused).
-    const uint32_t n_iter = gw < n_chunks ? (n_chunks - gw + n_warps - 1u) / n_warps : 0u;
+    // CONE: work item i = (live super-chunk i / 8, chunk i % 8 of it); the chunks behind the last full super-chunk follow
+    const uint32_t n_sc_items = CONE ? q.cone_cnt->n_live * ix::SC_CHUNKS : 0u;
+    const uint32_t tail_first = CONE ? p.cone_n_super * ix::SC_CHUNKS : 0u;
+    const uint32_t n_items = CONE ? n_sc_items + (n_chunks - tail_first) : n_chunks;
+    const uint32_t n_iter = gw < n_items ? (n_items - gw + n_warps - 1u) / n_warps : 0u;
     uint32_t rec_a = smem_u32(&ws.pipe.rec[0][lane]), xy_a = smem_u32(&ws.pipe.xy[0][0][lane]);
     asm volatile("" : "+r"(rec_a), "+r"(xy_a));
     const uint4* const rec_g = sc.rec + (size_t)gw * 32u + lane;
@@ -168,8 +265,34 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
         if (!BAND) return 1u;
         return (k < n_iter && !culled(gw + k * n_warps)) ? 1u : 0u;
     };
+    // CONE: lane l keeps the chunk of iteration cb + l (and of cb + 32 + l, loaded one block of 32 iterations ahead of
+    // its first use); c_fifo = chunks of the iterations k .. k + 4
+    uint32_t cb = 0, c_blk = 0, c_blk_next = 0;
+    auto chunk_of_iter = [&](uint32_t j) -> uint32_t {   // chunk of this warp's iteration j (clamped to its last one)
+        const uint32_t i = gw + min(j, n_iter - 1u) * n_warps;
+        return i < n_sc_items ? __ldg(q.live_sc + (i >> 3)) * ix::SC_CHUNKS + (i & (ix::SC_CHUNKS - 1u)) : tail_first + (i - n_sc_items);
+    };
+    auto chunk_lookup = [&](uint32_t j) -> uint32_t {    // j ascends by one from call to call
+        if (j - cb >= 32u) {
+            cb += 32u;
+            c_blk = c_blk_next;
+            c_blk_next = chunk_of_iter(cb + 32u + lane);
+        }
+        return __shfl_sync(0xFFFFFFFFu, c_blk, j - cb);
+    };
+    uint32_t c_f0 = 0, c_f1 = 0, c_f2 = 0, c_f3 = 0, c_f4 = 0;
+    if (CONE && n_iter) {
+        c_blk = chunk_of_iter(lane);
+        c_blk_next = chunk_of_iter(32u + lane);
+        c_f0 = chunk_lookup(0u); c_f1 = chunk_lookup(1u); c_f2 = chunk_lookup(2u); c_f3 = chunk_lookup(3u);
+    }
     auto fetch_rec = [&](uint32_t k, uint32_t slot) {   // record of iteration k -> ring slot
-        cp_async16(rec_a + (slot << 9), rec_g + (size_t)min(k, n_iter - 1u) * rec_step);
+        if (CONE) {
+            const uint32_t ck = k == 0u ? c_f0 : (k == 1u ? c_f1 : (k == 2u ? c_f2 : (k == 3u ? c_f3 : c_f4)));   // prologue: k < 4
+            cp_async16(rec_a + (slot << 9), sc.rec + (size_t)ck * 32u + lane);
+        } else {
+            cp_async16(rec_a + (slot << 9), rec_g + (size_t)min(k, n_iter - 1u) * rec_step);
+        }
     };
     auto gather_xy = [&](uint32_t slot) {   // (x', y') of the three corners of the record in ring slot `slot`
         const uint4 r = lds128(rec_a + (slot << 9));
@@ -193,7 +316,7 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     cp_async_commit();
 
     for (uint32_t k = 0; k < n_iter; ++k) {
-        const uint32_t c = gw + k * n_warps;
+        const uint32_t c = CONE ? c_f0 : gw + k * n_warps;
         const uint32_t ps = k & 3u;   // ring slot of this iteration's record and coordinates
         cp_async_wait<1>();   // everything committed two iterations ago has landed: coordinates k, record k + 2
         if (!BAND || (live & 4u)) gather_xy(ps ^ 2u);
@@ -434,6 +557,10 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
             const uint32_t l = is_live(k + 4u);
             live = (live >> 1) | (l << 3);
             if (l) fetch_rec(k + 4u, ps);
+        } else if (CONE) {
+            c_f4 = chunk_lookup(k + 4u);
+            cp_async16(rec_a + (ps << 9), sc.rec + (size_t)c_f4 * 32u + lane);
+            c_f0 = c_f1; c_f1 = c_f2; c_f2 = c_f3; c_f3 = c_f4;
         } else {
             fetch_rec(k + 4u, ps);
         }

@@ -14,7 +14,7 @@ import scenes as S
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["soup", "indexed", "indexed-tiles", "indexed-pairs"])
+@pytest.fixture(params=["soup", "indexed", "indexed-tiles", "indexed-pairs", "indexed-nocone"])
 def geom_path(request, monkeypatch):
     """Runs the test once per geometry path: SLOTH_PATH pins what every context created inside the test uses
     (1 = k_geom3 over the soup, 2 = k_xform + k_tri over the deduplicated vertices), whatever AUTO would pick;
@@ -23,6 +23,7 @@ def geom_path(request, monkeypatch):
     monkeypatch.setenv("SLOTH_PATH", "1" if request.param == "soup" else "2")
     monkeypatch.setenv("SLOTH_TILES", "2" if request.param.endswith("tiles") else "0")
     monkeypatch.setenv("SLOTH_TRI2", "1" if request.param.endswith("pairs") else "0")   # k_tri2: two chunks per warp turn
+    monkeypatch.setenv("SLOTH_CONE", "0" if request.param.endswith("nocone") else "1")  # 0: no super-chunk is skipped
     return request.param
 
 
