@@ -583,3 +583,42 @@ def test_span_wire_returns_the_same_cells():
             assert np.array_equal(small, ctx.render_batch(rots[:5])), name
         finally:
             ctx.close()
+
+
+def test_super_chunk_certificate_under_general_matrices():
+    """k_super_cert skips whole super-chunks of 256 triangles it can prove back-facing for the frame's matrix.  The
+    caller's `transform` is any 4x4 (draw_mesh takes it as is, rasterizer.rs:39-46): rotations, anisotropic scale,
+    shear, mirror images (which turn the back faces into front faces), translations that push the model half off the
+    frame, a collapsed axis.  Every frame must equal the oracle's, newline stamps included, and the plain rotations
+    must actually skip something."""
+    rng = np.random.default_rng(17)
+    xyz, rgb, s0 = meshes.icosphere(40)                  # 32 000 triangles = 125 super-chunks, ~1 cell each at 640x360
+    n_chunks = (len(xyz) + 31) // 32
+    ctx = rs.Context.blank(True)
+    try:
+        ctx.set_scene(xyz, rgb, s0)
+        ctx.resize(640, 360)
+        ctx.stats_enable(count_fragments=True)
+        skipped_some = 0
+        for k in range(14):
+            rot = oracle.rotation(*(rng.random(3) * 6.3)).reshape(4, 4).astype(np.float64)   # column-major
+            if k >= 3:
+                lin = np.diag(rng.uniform(0.3, 1.4, 3))
+                lin[0, 1] = rng.uniform(-0.6, 0.6)                                   # shear
+                if k % 3 == 0:
+                    lin[2, 2] = -lin[2, 2]                                           # mirror image
+                if k == 9:
+                    lin[1, :] = 0.0                                                  # collapsed axis: zero-area triangles
+                rot[:3, :3] = rot[:3, :3] @ lin
+                rot[3, :3] = rng.uniform(-0.7, 0.7, 3)                               # translation (last row, column-major)
+            rot = rot.astype(np.float32).reshape(16)
+            ocells, oz, ocnt = oracle.render(xyz, rgb, s0, 640, 360, rot, image=True, mode=0)
+            cells, z = ctx.render(rot, want_z=True)
+            st = ctx.stats()
+            assert_same(cells, z, ocells, oz, f"matrix {k}")
+            assert st["fragments"] == ocnt["covered"], k
+            if st["chunks_processed"] < n_chunks:
+                skipped_some += 1
+        assert skipped_some >= 3, skipped_some
+    finally:
+        ctx.close()
