@@ -30,6 +30,9 @@
 #include "tri2_kernel.cuh"
 #include "tile_kernels.cuh"
 #include "spans.cuh"
+#ifndef STAMP_BLOCKS_PER_SM
+#define STAMP_BLOCKS_PER_SM 4u
+#endif
 #include "../host/wire.hpp"
 #include "flush.cuh"
 #include "loader.cuh"
@@ -391,7 +394,7 @@ int enqueue_xform(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
 {
     const float* px = c->sc_pos;
     const uint32_t n_threads = (c->n_vert + 1 + XFORM_PER_THREAD - 1) / XFORM_PER_THREAD;
-    k_xform<<<(n_threads + 255) / 256, 256, 0, st>>>(p, px, px + c->pos_stride, px + 2 * c->pos_stride, c->n_vert, c->vxy[set],
+    k_xform<<<(n_threads + CO_THREADS - 1) / CO_THREADS, CO_THREADS, 0, st>>>(p, px, px + c->pos_stride, px + 2 * c->pos_stride, c->n_vert, c->vxy[set],
                                                      c->vz[set]);
     c->launches += 1;
     if (cone_frame(c, p)) {
@@ -598,7 +601,8 @@ int enqueue_tail(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st)
     if (c->indexed && cone_frame(c, p) && p.image && !(p.debug & 2u)) {
         // row stamps of the super-chunks k_super_cert took off k_tri's list (reads this set's transformed vertices:
         // the transform of the frame after next waits for ev_stamped)
-        k_super_stamp<<<(c->n_super + 7) / 8, 256, 0, st>>>(p, c->sc_super_ids, c->vxy[set], q);
+        // a few warps per SM walk the skip list (its length is only known on the device)
+        k_super_stamp<<<std::min<uint32_t>((c->n_super + 3) / 4, (uint32_t)c->sm_count * STAMP_BLOCKS_PER_SM), 128, 0, st>>>(p, c->sc_super_ids, c->vxy[set], q);
         c->launches += 1;
         CU(cudaEventRecord(c->ev_stamped[set], st));
     }
@@ -638,7 +642,7 @@ int enqueue_resolve(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st
         // a warp owns 32 * RESOLVE_SLOTS consecutive slots
         const uint32_t per_warp = 32u * RESOLVE_SLOTS;
         const uint32_t n_threads = std::max<uint32_t>((n_slots + per_warp - 1) / per_warp * 32u, n_tail ? 32u : 0u);
-        if (n_threads) k_resolve_even<<<(n_threads + 255) / 256, 256, 0, st>>>(p, sc, c->keys[set], q, d_out, n_slots, n_tail);
+        if (n_threads) k_resolve_even<<<(n_threads + CO_THREADS - 1) / CO_THREADS, CO_THREADS, 0, st>>>(p, sc, c->keys[set], q, d_out, n_slots, n_tail);
         c->launches += 1;
     } else {
         const uint32_t n_cells = rows * c->W;

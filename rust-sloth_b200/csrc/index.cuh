@@ -411,30 +411,41 @@ __global__ void __launch_bounds__(256) k_ix_expand_input(const float* __restrict
 // k_tri at one block per SM.  Slot n_vert is the sentinel the padding records point at: far off-screen, no rows,
 // no candidates.  The position arrays and the outputs are padded to whole groups of four.
 // ---------------------------------------------------------------------------------
-static constexpr uint32_t XFORM_PER_THREAD = 4;
+#ifndef XFORM_VERTS_PER_THREAD
+#define XFORM_VERTS_PER_THREAD 4
+#endif
+static constexpr uint32_t XFORM_PER_THREAD = XFORM_VERTS_PER_THREAD;   // a multiple of 4
 
 __global__ void __launch_bounds__(256) k_xform(const __grid_constant__ FrameParams p, const float* __restrict__ px,
                                                const float* __restrict__ py, const float* __restrict__ pz, uint32_t n_vert,
                                                float2* __restrict__ vxy, float* __restrict__ vz)
 {
-    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * XFORM_PER_THREAD;
-    if (i > n_vert) return;
-    const float4 X = __ldcs(reinterpret_cast<const float4*>(px + i));
-    const float4 Y = __ldcs(reinterpret_cast<const float4*>(py + i));
-    const float4 Z = __ldcs(reinterpret_cast<const float4*>(pz + i));
-    const float x[4] = {X.x, X.y, X.z, X.w}, y[4] = {Y.x, Y.y, Y.z, Y.w}, z[4] = {Z.x, Z.y, Z.z, Z.w};
-    float ox[4], oy[4], oz[4];
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * XFORM_PER_THREAD;
+    if (i0 > n_vert) return;
+    float4 X[XFORM_PER_THREAD / 4], Y[XFORM_PER_THREAD / 4], Z[XFORM_PER_THREAD / 4];
 #pragma unroll
-    for (uint32_t k = 0; k < 4u; ++k) {
-        ox[k] = xform_row(p.m + 0, x[k], y[k], z[k]);
-        oy[k] = xform_row(p.m + 4, x[k], y[k], z[k]);
-        oz[k] = xform_row(p.m + 8, x[k], y[k], z[k]);
-        if (i + k >= n_vert) { ox[k] = oy[k] = -1.0e30f; oz[k] = 0.0f; }   // the sentinel (and the padding after it)
+    for (uint32_t g = 0; g < XFORM_PER_THREAD / 4; ++g) {   // all loads first: the kernel is latency, not arithmetic
+        X[g] = __ldcs(reinterpret_cast<const float4*>(px + i0 + 4u * g));
+        Y[g] = __ldcs(reinterpret_cast<const float4*>(py + i0 + 4u * g));
+        Z[g] = __ldcs(reinterpret_cast<const float4*>(pz + i0 + 4u * g));
     }
-    float4* oxy = reinterpret_cast<float4*>(vxy + i);
-    oxy[0] = make_float4(ox[0], oy[0], ox[1], oy[1]);
-    oxy[1] = make_float4(ox[2], oy[2], ox[3], oy[3]);
-    *reinterpret_cast<float4*>(vz + i) = make_float4(oz[0], oz[1], oz[2], oz[3]);
+#pragma unroll
+    for (uint32_t g = 0; g < XFORM_PER_THREAD / 4; ++g) {
+        const uint32_t i = i0 + 4u * g;
+        const float x[4] = {X[g].x, X[g].y, X[g].z, X[g].w}, y[4] = {Y[g].x, Y[g].y, Y[g].z, Y[g].w}, z[4] = {Z[g].x, Z[g].y, Z[g].z, Z[g].w};
+        float ox[4], oy[4], oz[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; ++k) {
+            ox[k] = xform_row(p.m + 0, x[k], y[k], z[k]);
+            oy[k] = xform_row(p.m + 4, x[k], y[k], z[k]);
+            oz[k] = xform_row(p.m + 8, x[k], y[k], z[k]);
+            if (i + k >= n_vert) { ox[k] = oy[k] = -1.0e30f; oz[k] = 0.0f; }   // the sentinel (and the padding after it)
+        }
+        float4* oxy = reinterpret_cast<float4*>(vxy + i);
+        oxy[0] = make_float4(ox[0], oy[0], ox[1], oy[1]);
+        oxy[1] = make_float4(ox[2], oy[2], ox[3], oy[3]);
+        *reinterpret_cast<float4*>(vz + i) = make_float4(oz[0], oz[1], oz[2], oz[3]);
+    }
 }
 
 }  // namespace sloth

@@ -656,7 +656,15 @@ SLOTH_DEV bool stamp_beats_fragment(const FrameParams& p, const Scene& sc, const
 // geometry kernel, where only instruction-level parallelism hides the latency.  Row / column of a slot cost one
 // division per thread instead of one per slot; the newline-order check (warp-cooperative) is only entered when
 // some lane of the warp has a contested cell.
-static constexpr uint32_t RESOLVE_SLOTS = 4;   // per thread
+#ifndef RESOLVE_SLOTS_PER_THREAD
+#define RESOLVE_SLOTS_PER_THREAD 4
+#endif
+static constexpr uint32_t RESOLVE_SLOTS = RESOLVE_SLOTS_PER_THREAD;   // per thread
+// threads per block of the kernels that run beside the triangle kernel of a neighbouring frame (k_xform, k_resolve_even):
+// what is left of an SM next to three k_tri blocks is 10 K registers
+#ifndef CO_THREADS
+#define CO_THREADS 128
+#endif
 
 __global__ void __launch_bounds__(256) k_resolve_even(const __grid_constant__ FrameParams p, const Scene sc,
                                                       unsigned long long* __restrict__ keys, const Queues q,

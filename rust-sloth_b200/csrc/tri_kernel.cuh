@@ -37,7 +37,8 @@ static constexpr uint32_t T_WARPS = T_WARPS_PER_BLOCK;     // warps per block
 #define T_BLOCKS_PER_SM 3      // persistent blocks per SM (shared memory: 3 x 60 KB)
 #endif
 #ifndef T_REG_BLOCKS
-#define T_REG_BLOCKS 3         // register budget = 65536 / (256 * T_REG_BLOCKS)
+#define T_REG_BLOCKS 4         // register budget = 65536 / (256 * T_REG_BLOCKS): 64 registers, so that three resident blocks leave 16 K
+                               // registers to the neighbouring frames' kernels (k_xform, k_tail, k_resolve): 142 -> 133 us per frame in batches
 #endif
 static constexpr uint32_t T_RING = 64;     // per-warp ring of covered fragments (power of two, >= 2 * 32)
 static constexpr uint32_t T_STAGES = 4;     // ring depth of the cp.async pipeline (records and coordinates)
@@ -192,18 +193,19 @@ SLOTH_DEV void super_rows(const FrameParams& p, const uint32_t* __restrict__ ids
 // k_super_stamp (image mode, after k_tri, before the resolve of the same frame): one warp per entry of the skip list,
 // taken from the end -- the list is roughly ascending, so the highest indices reach a row first and most later
 // entries find it stamped already (one load instead of an atomic on a contended word).
-__global__ void __launch_bounds__(256) k_super_stamp(const __grid_constant__ FrameParams p, const uint32_t* __restrict__ ids,
+__global__ void __launch_bounds__(128) k_super_stamp(const __grid_constant__ FrameParams p, const uint32_t* __restrict__ ids,
                                                      const float2* __restrict__ vxy, const Queues q)
 {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t i = blockIdx.x * 8u + (threadIdx.x >> 5), n_skip = q.cone_cnt->n_skip;
-    if (i >= n_skip) return;
-    const uint32_t s_c = q.skip_sc[n_skip - 1u - i];
-    uint32_t lo, hi;
-    super_rows(p, ids, vxy, s_c, lane, lo, hi);
-    const uint32_t value = s_c * ix::SC_CHUNKS + ix::SC_CHUNKS;   // 1 + index of its last chunk
-    for (uint32_t r = lo + lane; r < hi; r += 32u)
-        if (__ldcg(q.rowmax + r) < value) atomicMax(q.rowmax + r, value);
+    const uint32_t lane = threadIdx.x & 31u, wpb = blockDim.x >> 5;
+    const uint32_t n_skip = q.cone_cnt->n_skip, n_warps = gridDim.x * wpb;
+    for (uint32_t i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n_skip; i += n_warps) {
+        const uint32_t s_c = q.skip_sc[n_skip - 1u - i];
+        uint32_t lo, hi;
+        super_rows(p, ids, vxy, s_c, lane, lo, hi);
+        const uint32_t value = s_c * ix::SC_CHUNKS + ix::SC_CHUNKS;   // 1 + index of its last chunk
+        for (uint32_t r = lo + lane; r < hi; r += 32u)
+            if (__ldcg(q.rowmax + r) < value) atomicMax(q.rowmax + r, value);
+    }
 }
 
 // Dynamic shared memory of one block: [rowmax copy (ROWMAX_SHARED)] [TWarpSmem x T_WARPS]
