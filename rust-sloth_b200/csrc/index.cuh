@@ -6,7 +6,9 @@
 // are therefore deduplicated by exact bit pattern (so -0.0 / +0.0 and NaN payloads stay distinct) into
 //   pos    unique vertices, SoA x[] y[] z[], numbered in order of first appearance in the draw order
 //          (neighbours in the soup stay neighbours in memory)
-//   rec    one uint4 per triangle: (i0, i1, i2, 0), padded to a multiple of 32 triangles with a sentinel vertex
+//   rec    one uint4 per triangle: (i0, i1, i2, triangle << 1 | chunk-connected flag), padded to a multiple of 32
+//          triangles with a sentinel vertex -- the record names its own triangle, so a parked fragment is the
+//          record itself (one 16-byte shared-memory store) and k_tri carries no chunk index through its pipeline
 // and every frame runs k_xform (one thread per unique vertex, same xform_row order as the soup path) before the
 // triangle kernel k_tri gathers (x', y') -- and (z') only for covering triangles.
 //
@@ -192,14 +194,14 @@ __global__ void __launch_bounds__(256) k_ix_rank(const Scene sc, const uint32_t*
     }
 }
 
-// rec[t] = (vertex ids of the three corners, 0); triangles [n_tri, n_padded) reference the sentinel vertex
+// rec[t] = (vertex ids of the three corners, t << 1); triangles [n_tri, n_padded) reference the sentinel vertex
 __global__ void __launch_bounds__(256) k_ix_records(const uint32_t* __restrict__ rep, const uint32_t* __restrict__ rank, uint32_t n_tri,
                                                     uint32_t n_padded, uint32_t sentinel, uint4* __restrict__ rec)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_padded) return;
-    if (t >= n_tri) { rec[t] = make_uint4(sentinel, sentinel, sentinel, 0u); return; }
-    rec[t] = make_uint4(rank[rep[3u * t]], rank[rep[3u * t + 1u]], rank[rep[3u * t + 2u]], 0u);
+    if (t >= n_tri) { rec[t] = make_uint4(sentinel, sentinel, sentinel, t << 1); return; }
+    rec[t] = make_uint4(rank[rep[3u * t]], rank[rep[3u * t + 1u]], rank[rep[3u * t + 2u]], t << 1);
 }
 
 // Connectivity flag of every chunk of 32 triangles (bit 0 of rec[..].w, same value in all 32 records): set when the
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(256) k_ix_connectivity(uint4* __restrict__ rec
         if (!__any_sync(0xFFFFFFFFu, label != before)) break;
     }
     const bool one = full && __all_sync(0xFFFFFFFFu, label == 0u);
-    r.w = one ? 1u : 0u;
+    r.w = (t << 1) | (one ? 1u : 0u);   // t < 2^27 (sloth_scene_set refuses larger scenes)
     rec[t] = r;
 }
 

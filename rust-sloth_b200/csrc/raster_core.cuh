@@ -68,7 +68,7 @@ struct Scene {
     const uint32_t* __restrict__ rgb; // r | g<<8 | b<<16
     const float4* __restrict__ bounds; // per chunk of 32 triangles: bounding sphere (centre.xyz, radius), object space
     // indexed path (index.cuh): per-triangle vertex ids, and the per-frame output of k_xform
-    const uint4* __restrict__ rec;     // (i0, i1, i2, 0) per triangle, padded to a multiple of 32 with the sentinel vertex
+    const uint4* __restrict__ rec;     // (i0, i1, i2, triangle << 1 | connected) per triangle, padded to a multiple of 32 with the sentinel vertex
     const float2* __restrict__ vxy;    // (x', y') per unique vertex
     const float* __restrict__ vz;      // z' per unique vertex
     const uint32_t* __restrict__ super_ids;   // unique vertex ids of every super-chunk of 256 triangles (index.cuh), SC_IDS each

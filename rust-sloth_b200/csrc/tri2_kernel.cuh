@@ -285,9 +285,7 @@ k_tri2(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long
                     const unsigned who = __ballot_sync(0xFFFFFFFFu, has);
                     if (has) {
                         const uint32_t slot = (q_head + q_count + __popc(who & ((1u << lane) - 1u))) & (T_RING - 1u);
-                        const uint4 r = lds128(ra);
-                        wq.i0[slot] = r.x; wq.i1[slot] = r.y; wq.i2[slot] = r.z;
-                        wq.tri[slot] = t;
+                        wq.rec[slot] = lds128(ra);   // the record names its triangle (index.cuh)
                         wq.xy[slot] = (minx + (bit & 7u)) | ((miny + (bit >> 3)) << 16);
                     }
                     q_count += __popc(who);
@@ -342,9 +340,7 @@ k_tri2(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long
                 const unsigned who = __ballot_sync(0xFFFFFFFFu, has);
                 if (has) {
                     const uint32_t slot = (q_head + q_count + __popc(who & ((1u << lane) - 1u))) & (T_RING - 1u);
-                    const uint4 r = lds128(ra);
-                    wq.i0[slot] = r.x; wq.i1[slot] = r.y; wq.i2[slot] = r.z;
-                    wq.tri[slot] = t;
+                    wq.rec[slot] = lds128(ra);
                     wq.xy[slot] = xy0 + bit + (bit >= 3u ? 65536u - 3u : 0u);   // bit = row * 3 + column
                 }
                 q_count += __popc(who);

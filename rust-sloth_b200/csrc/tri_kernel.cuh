@@ -40,12 +40,17 @@ static constexpr uint32_t T_WARPS = T_WARPS_PER_BLOCK;     // warps per block
 #define T_REG_BLOCKS 4         // register budget = 65536 / (256 * T_REG_BLOCKS): 64 registers, so that three resident blocks leave 16 K
                                // registers to the neighbouring frames' kernels (k_xform, k_tail, k_resolve): 142 -> 133 us per frame in batches
 #endif
+// SLOTH_DEBUG bits 1, 3 and 4 (no stamps / park without emitting / stop after the back-face proof) are timing experiments
+// that cost k_tri's inner loop a constant load and a test each per chunk: compiled in only with -DSLOTH_TRI_KNOBS=1
+#ifndef SLOTH_TRI_KNOBS
+#define SLOTH_TRI_KNOBS 0
+#endif
 static constexpr uint32_t T_RING = 64;     // per-warp ring of covered fragments (power of two, >= 2 * 32)
 static constexpr uint32_t T_STAGES = 4;     // ring depth of the cp.async pipeline (records and coordinates)
 
+// a parked fragment = its triangle's record as it came from memory (i0, i1, i2, triangle << 1 | flag) + the candidate
 struct TRing {
-    uint32_t i0[T_RING], i1[T_RING], i2[T_RING];
-    uint32_t tri[T_RING];
+    uint4 rec[T_RING];
     uint32_t xy[T_RING];      // x | y << 16
 };
 
@@ -81,6 +86,11 @@ SLOTH_DEV uint32_t lds32(uint32_t a)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+SLOTH_DEV void sts128(uint32_t a, const uint4& v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+SLOTH_DEV void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 SLOTH_DEV float2 lds64f(uint32_t a)
 {
     float2 v;
@@ -91,16 +101,31 @@ SLOTH_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "me
 template <int N>
 SLOTH_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// cov |= BIT when none of the three edge values fl(a_i - b_i) is negative, i.e. when no a_i < b_i (finite operands):
+// three chained compares and one predicated OR (written out because the compiler's own version needs selects)
+template <int BIT>
+SLOTH_DEV void cov_test(uint32_t& cov, float a0, float b0, float a1, float b1, float a2, float b2)
+{
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.geu.f32 p, %1, %2;\n\t"
+        "setp.geu.and.f32 p, %3, %4, p;\n\t"
+        "setp.geu.and.f32 p, %5, %6, p;\n\t"
+        "@p or.b32 %0, %0, %7;\n\t}"
+        : "+r"(cov)
+        : "f"(a0), "f"(b0), "f"(a1), "f"(b1), "f"(a2), "f"(b2), "n"(BIT));
+}
+
 // Emit `count` parked fragments starting at ring position `head`, lane = fragment.
 SLOTH_DEV void t_emit(const FrameParams& p, const Scene& sc, const TRing& wq, uint32_t head, uint32_t count, uint32_t lane,
                       unsigned long long* __restrict__ keys)
 {
-    if (lane >= count || (p.debug & 8u)) return;
+    if (lane >= count || (SLOTH_TRI_KNOBS && (p.debug & 8u))) return;
     const uint32_t slot = (head + lane) & (T_RING - 1u);
-    const uint32_t i0 = wq.i0[slot], i1 = wq.i1[slot], i2 = wq.i2[slot];
+    const uint4 r = wq.rec[slot];
+    const uint32_t i0 = r.x, i1 = r.y, i2 = r.z;
     const float2 P1 = __ldg(sc.vxy + i0), P2 = __ldg(sc.vxy + i1), P3 = __ldg(sc.vxy + i2);
     const float z1 = __ldg(sc.vz + i0), z2 = __ldg(sc.vz + i1), z3 = __ldg(sc.vz + i2);
-    const uint32_t tri = wq.tri[slot], xy = wq.xy[slot];
+    const uint32_t tri = r.w >> 1, xy = wq.xy[slot];
     Setup s;
     s.x1 = P1.x; s.y1 = P1.y; s.z1 = z1;
     s.x2 = P2.x; s.y2 = P2.y; s.z2 = z2;
@@ -228,8 +253,10 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     const uint32_t n_chunks = (p.n_tri + 31u) >> 5;
     const uint32_t n_warps = gridDim.x * T_WARPS;
     const uint32_t gw = blockIdx.x * T_WARPS + warp;
-    uint32_t q_head = 0, q_count = 0, nfrag_count = 0, chunks_done = 0;   // warp-uniform
-    const bool do_stamps = p.image && !(p.debug & 2u);
+    // fragment ring, absolute counters (warp-uniform): q_tail fragments parked so far, q_lim - 32 of them emitted; entry i
+    // lives in slot i mod T_RING.  Fewer than 32 wait at any time, at most 32 arrive per turn.
+    uint32_t q_tail = 0, q_lim = 32u, chunks_done = 0;
+    const bool do_stamps = p.image && !(SLOTH_TRI_KNOBS && (p.debug & 2u));
     if (ROWMAX_SHARED && do_stamps)
         for (uint32_t i = threadIdx.x; i < n_rowmax; i += blockDim.x) s_rowmax[i] = 0u;
     __syncthreads();
@@ -260,7 +287,8 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     const uint32_t n_items = CONE ? n_sc_items + (n_chunks - tail_first) : n_chunks;
     const uint32_t n_iter = gw < n_items ? (n_items - gw + n_warps - 1u) / n_warps : 0u;
     uint32_t rec_a = smem_u32(&ws.pipe.rec[0][lane]), xy_a = smem_u32(&ws.pipe.xy[0][0][lane]);
-    asm volatile("" : "+r"(rec_a), "+r"(xy_a));
+    uint32_t ring_a = smem_u32(&wq.rec[0]);   // wq.xy follows at + 16 * T_RING
+    asm volatile("" : "+r"(rec_a), "+r"(xy_a), "+r"(ring_a));
     const uint4* const rec_g = sc.rec + (size_t)gw * 32u + lane;
     const uint32_t rec_step = n_warps * 32u;   // records between consecutive chunks of this warp
     auto is_live = [&](uint32_t k) -> uint32_t {
@@ -268,7 +296,7 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
         return (k < n_iter && !culled(gw + k * n_warps)) ? 1u : 0u;
     };
     // CONE: lane l keeps the chunk of iteration cb + l (and of cb + 32 + l, loaded one block of 32 iterations ahead of
-    // its first use); c_fifo = chunks of the iterations k .. k + 4
+    // its first use).  The chunk index is only needed to fetch the record: the record names its own triangle.
     uint32_t cb = 0, c_blk = 0, c_blk_next = 0;
     auto chunk_of_iter = [&](uint32_t j) -> uint32_t {   // chunk of this warp's iteration j (clamped to its last one)
         const uint32_t i = gw + min(j, n_iter - 1u) * n_warps;
@@ -282,19 +310,13 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
         }
         return __shfl_sync(0xFFFFFFFFu, c_blk, j - cb);
     };
-    uint32_t c_f0 = 0, c_f1 = 0, c_f2 = 0, c_f3 = 0, c_f4 = 0;
     if (CONE && n_iter) {
         c_blk = chunk_of_iter(lane);
         c_blk_next = chunk_of_iter(32u + lane);
-        c_f0 = chunk_lookup(0u); c_f1 = chunk_lookup(1u); c_f2 = chunk_lookup(2u); c_f3 = chunk_lookup(3u);
     }
-    auto fetch_rec = [&](uint32_t k, uint32_t slot) {   // record of iteration k -> ring slot
-        if (CONE) {
-            const uint32_t ck = k == 0u ? c_f0 : (k == 1u ? c_f1 : (k == 2u ? c_f2 : (k == 3u ? c_f3 : c_f4)));   // prologue: k < 4
-            cp_async16(rec_a + (slot << 9), sc.rec + (size_t)ck * 32u + lane);
-        } else {
-            cp_async16(rec_a + (slot << 9), rec_g + (size_t)min(k, n_iter - 1u) * rec_step);
-        }
+    auto fetch_rec = [&](uint32_t k, uint32_t slot) {   // record of iteration k -> ring slot (k ascends by one from call to call)
+        if (CONE) cp_async16(rec_a + (slot << 9), sc.rec + (size_t)chunk_lookup(k) * 32u + lane);
+        else cp_async16(rec_a + (slot << 9), rec_g + (size_t)min(k, n_iter - 1u) * rec_step);
     };
     auto gather_xy = [&](uint32_t slot) {   // (x', y') of the three corners of the record in ring slot `slot`
         const uint4 r = lds128(rec_a + (slot << 9));
@@ -318,14 +340,14 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     cp_async_commit();
 
     for (uint32_t k = 0; k < n_iter; ++k) {
-        const uint32_t c = CONE ? c_f0 : gw + k * n_warps;
         const uint32_t ps = k & 3u;   // ring slot of this iteration's record and coordinates
         cp_async_wait<1>();   // everything committed two iterations ago has landed: coordinates k, record k + 2
         if (!BAND || (live & 4u)) gather_xy(ps ^ 2u);
         uint32_t mask = 0, minx = 0, miny = 0;
-        const uint32_t t = c * 32u + lane;
         if (!BAND || (live & 1u)) {
-        if (p.count_frags) ++chunks_done;
+        if (BAND) ++chunks_done;
+        const uint32_t rec_w = lds32(rec_a + (ps << 9) + 12u);   // triangle << 1 | chunk-connected flag (index.cuh)
+        const uint32_t t = rec_w >> 1, c = t >> 5;
         const float2 P1 = lds64f(xy_a + ps * 768u), P2 = lds64f(xy_a + ps * 768u + 256u), P3 = lds64f(xy_a + ps * 768u + 512u);
         const float x1 = P1.x, y1 = P1.y, x2 = P2.x, y2 = P2.y, x3 = P3.x, y3 = P3.y;
 
@@ -344,7 +366,7 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
         // A chunk whose 32 triangles hang together through shared vertices (flag in the record, set at scene-set)
         // stamps exactly the rows [min miny, max maxy): the y-ranges of triangles that share a vertex overlap or
         // touch, so the union of the chunk's ranges has no gap, and ceil() commutes with min / max.
-        const bool connected = !BAND && !CHECK_REGULAR && (lds32(rec_a + (ps << 9) + 12u) & 1u) != 0u;   // warp-uniform
+        const bool connected = !BAND && !CHECK_REGULAR && (rec_w & 1u) != 0u;   // warp-uniform
         if (do_stamps && connected) {
             const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, miny);
             const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, maxy);
@@ -380,7 +402,7 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
             back = T > 1e-30f && area < -T;
         }
         // chunks on the far side of a closed mesh end here (after the stamps); so do empty ones
-        const bool maybe = has_rows && (CHECK_REGULAR ? (!regular || !back) : !back) && !(p.debug & 16u);
+        const bool maybe = has_rows && (CHECK_REGULAR ? (!regular || !back) : !back) && !(SLOTH_TRI_KNOBS && (p.debug & 16u));
         if (__any_sync(0xFFFFFFFFu, maybe || tall)) {
             minx = __float2uint_rz(ceilf(fmaxf(mn0, 1.0f)));
             const uint32_t maxx = __float2uint_rz(ceilf(fminf(mul(mx0, 2.0f), p.wm1)));
@@ -410,14 +432,15 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
                     gc[k][2] = mul(dy2, sub(px, x1));
                 }
                 uint32_t cov = 0;
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        // regular triangle: no NaN, so "all >= 0" == "none < 0"
-                        const float w0 = sub(cr[r][0], gc[k][0]), w1 = sub(cr[r][1], gc[k][1]), w2 = sub(cr[r][2], gc[k][2]);
-                        if (!(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f)) cov |= 1u << (r * 3 + k);
-                    }
+                // regular triangle: no NaN, so "all >= 0" == "none < 0"; and the edge value w = fl(cr - gc) is negative
+                // exactly when cr < gc: both are finite, a non-zero difference of two floats is at least 2^-149 in
+                // magnitude and denormals are kept, so rounding never changes its sign or makes it zero
+                cov_test<1>(cov, cr[0][0], gc[0][0], cr[0][1], gc[0][1], cr[0][2], gc[0][2]);
+                cov_test<2>(cov, cr[0][0], gc[1][0], cr[0][1], gc[1][1], cr[0][2], gc[1][2]);
+                cov_test<4>(cov, cr[0][0], gc[2][0], cr[0][1], gc[2][1], cr[0][2], gc[2][2]);
+                cov_test<8>(cov, cr[1][0], gc[0][0], cr[1][1], gc[0][1], cr[1][2], gc[0][2]);
+                cov_test<16>(cov, cr[1][0], gc[1][0], cr[1][1], gc[1][1], cr[1][2], gc[1][2]);
+                cov_test<32>(cov, cr[1][0], gc[2][0], cr[1][1], gc[2][1], cr[1][2], gc[2][2]);
                 const uint32_t cm = (1u << min(span, 3u)) - 1u;
                 const uint32_t valid = cm | (rows > 1u ? cm << 3 : 0u);
                 // a row is finished after column 2 if a closing edge (dy >= 0) fails there
@@ -426,9 +449,9 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
                     const bool nd0 = !(dy0 < 0.0f), nd1 = !(dy1 < 0.0f), nd2 = !(dy2 < 0.0f);
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
-                        const bool closed = (nd0 && sub(cr[r][0], gc[2][0]) < 0.0f) || (nd1 && sub(cr[r][1], gc[2][1]) < 0.0f) ||
-                                            (nd2 && sub(cr[r][2], gc[2][2]) < 0.0f);
-                        if ((uint32_t)r < rows && !closed) open = true;
+                        // (bitwise on purpose: predicate logic instead of a chain of branches)
+                        const bool closed = (nd0 & (cr[r][0] < gc[2][0])) | (nd1 & (cr[r][1] < gc[2][1])) | (nd2 & (cr[r][2] < gc[2][2]));
+                        open |= ((uint32_t)r < rows) & !closed;
                     }
                 }
                 if (foot) {
@@ -475,20 +498,16 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
                     m64 &= m64 - 1ull;
                     const unsigned who = __ballot_sync(0xFFFFFFFFu, has);
                     if (has) {
-                        const uint32_t slot = (q_head + q_count + __popc(who & ((1u << lane) - 1u))) & (T_RING - 1u);
-                        const uint4 r = lds128(rec_a + (ps << 9));
-                        wq.i0[slot] = r.x; wq.i1[slot] = r.y; wq.i2[slot] = r.z;
-                        wq.tri[slot] = t;
+                        const uint32_t slot = (q_tail + __popc(who & ((1u << lane) - 1u))) & (T_RING - 1u);
+                        wq.rec[slot] = lds128(rec_a + (ps << 9));
                         wq.xy[slot] = (minx + (bit & 7u)) | ((miny + (bit >> 3)) << 16);
                     }
-                    q_count += __popc(who);
-                    if (p.count_frags) nfrag_count += __popc(who);
-                    if (q_count >= 32u) {
+                    q_tail += __popc(who);
+                    if (q_tail >= q_lim) {
                         __syncwarp();
-                        t_emit(p, sc, wq, q_head, 32u, lane, keys);
+                        t_emit(p, sc, wq, q_lim - 32u, 32u, lane, keys);
                         __syncwarp();
-                        q_head = (q_head + 32u) & (T_RING - 1u);
-                        q_count -= 32u;
+                        q_lim += 32u;
                     }
                 }
                 // tier 3: row-band work items for k_tail, one warp-aggregated atomic
@@ -526,32 +545,35 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
 
         }   // live chunk
 
-        // ---- phase C: park the covered fragments of the 2 x 3 footprint, one per lane and turn; every 32
-        // parked fragments are emitted with all lanes busy ---------------------------------------------
-        const uint32_t xy0 = minx | (miny << 16);
-        while (__any_sync(0xFFFFFFFFu, mask != 0u)) {
-            const bool has = mask != 0u;
-            const uint32_t bit = (uint32_t)__ffs((int)mask) - 1u;   // garbage when !has, unused
-            mask &= mask - 1u;
-            const unsigned who = __ballot_sync(0xFFFFFFFFu, has);
-            if (has) {
-                const uint32_t slot = (q_head + q_count + __popc(who & ((1u << lane) - 1u))) & (T_RING - 1u);
-                const uint4 r = lds128(rec_a + (ps << 9));
-                wq.i0[slot] = r.x; wq.i1[slot] = r.y; wq.i2[slot] = r.z;
-                wq.tri[slot] = t;
-                wq.xy[slot] = xy0 + bit + (bit >= 3u ? 65536u - 3u : 0u);   // bit = row * 3 + column
-            }
-            q_count += __popc(who);
-            if (p.count_frags) nfrag_count += __popc(who);
-            if (q_count >= 32u) {
-                __syncwarp();
-                t_emit(p, sc, wq, q_head, 32u, lane, keys);
-                __syncwarp();
-                q_head = (q_head + 32u) & (T_RING - 1u);
-                q_count -= 32u;
-            }
+        // ---- phase C: park the covered fragments of the 2 x 3 footprint, one per lane and turn (most chunks need one
+        // turn, few more than two): the record as it stands in the pipeline ring (one 16-byte store) and the candidate.
+        // Every 32 parked fragments are emitted with all lanes busy.
+        unsigned who = __ballot_sync(0xFFFFFFFFu, mask != 0u);
+        if (who) {
+            const uint32_t xy0 = minx | (miny << 16);
+            const uint4 r = lds128(rec_a + (ps << 9));
+            const unsigned below = (1u << lane) - 1u;
+            do {
+                const bool has = mask != 0u;
+                const uint32_t bit = (uint32_t)__ffs((int)mask) - 1u;   // row * 3 + column; garbage when !has, unused
+                mask &= mask - 1u;
+                uint32_t o16;   // byte offset of the ring entry (opaque to the compiler, which otherwise goes back to a slot
+                                // index and shifts it twice)
+                asm("and.b32 %0, %1, %2;" : "=r"(o16) : "r"((q_tail + __popc(who & below)) << 4), "n"(T_RING * 16u - 16u));
+                if (has) {
+                    sts128(ring_a + o16, r);
+                    sts32(ring_a + T_RING * 16u + (o16 >> 2), xy0 + bit + (bit >= 3u ? 65536u - 3u : 0u));
+                }
+                q_tail += __popc(who);
+                if (q_tail >= q_lim) {
+                    __syncwarp();
+                    t_emit(p, sc, wq, q_lim - 32u, 32u, lane, keys);
+                    __syncwarp();
+                    q_lim += 32u;
+                }
+                who = __ballot_sync(0xFFFFFFFFu, mask != 0u);
+            } while (who);
         }
-
 
         // ---- record of iteration k + 4 (same ring slot as record k, which the parking above was the last to
         // read), then one commit for everything this iteration started
@@ -559,19 +581,16 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
             const uint32_t l = is_live(k + 4u);
             live = (live >> 1) | (l << 3);
             if (l) fetch_rec(k + 4u, ps);
-        } else if (CONE) {
-            c_f4 = chunk_lookup(k + 4u);
-            cp_async16(rec_a + (ps << 9), sc.rec + (size_t)c_f4 * 32u + lane);
-            c_f0 = c_f1; c_f1 = c_f2; c_f2 = c_f3; c_f3 = c_f4;
         } else {
             fetch_rec(k + 4u, ps);
         }
         cp_async_commit();
     }
     cp_async_wait<0>();
-    if (q_count) {
+    if (!BAND) chunks_done = n_iter;
+    if (q_tail != q_lim - 32u) {
         __syncwarp();
-        t_emit(p, sc, wq, q_head, q_count, lane, keys);
+        t_emit(p, sc, wq, q_lim - 32u, q_tail - (q_lim - 32u), lane, keys);
     }
     if (ROWMAX_SHARED && do_stamps) {   // publish this block's stamps (the probe skips most atomics)
         __syncthreads();
@@ -589,7 +608,7 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
         }
     }
     if (p.count_frags && lane == 0) {
-        if (nfrag_count) atomicAdd(&q.aux->frag_counter, (unsigned long long)nfrag_count);
+        if (q_tail) atomicAdd(&q.aux->frag_counter, (unsigned long long)q_tail);
         if (chunks_done) atomicAdd(&q.aux->chunks_done, chunks_done);
     }
 }
