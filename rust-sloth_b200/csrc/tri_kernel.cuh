@@ -57,7 +57,8 @@ struct TRing {
 // per-warp landing zone of the cp.async pipeline; lane l only ever touches [..][l]
 struct TPipe {
     uint4 rec[T_STAGES][32];        // 512 B per stage
-    float2 xy[T_STAGES][3][32];     // 768 B per stage
+    float2 xy[3][T_STAGES][32];     // corner-major: stage s at s * 256 in each corner's KB, so that the slots of k and k + 2
+                                    // are one XOR apart like the records'
 };
 
 struct TWarpSmem {
@@ -320,9 +321,9 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     };
     auto gather_xy = [&](uint32_t slot) {   // (x', y') of the three corners of the record in ring slot `slot`
         const uint4 r = lds128(rec_a + (slot << 9));
-        cp_async8(xy_a + slot * 768u, sc.vxy + r.x);
-        cp_async8(xy_a + slot * 768u + 256u, sc.vxy + r.y);
-        cp_async8(xy_a + slot * 768u + 512u, sc.vxy + r.z);
+        cp_async8(xy_a + (slot << 8), sc.vxy + r.x);
+        cp_async8(xy_a + (slot << 8) + 1024u, sc.vxy + r.y);
+        cp_async8(xy_a + (slot << 8) + 2048u, sc.vxy + r.z);
     };
     uint32_t live = 0;
     if (n_iter) {
@@ -348,7 +349,7 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
         if (BAND) ++chunks_done;
         const uint32_t rec_w = lds32(rec_a + (ps << 9) + 12u);   // triangle << 1 | chunk-connected flag (index.cuh)
         const uint32_t t = rec_w >> 1, c = t >> 5;
-        const float2 P1 = lds64f(xy_a + ps * 768u), P2 = lds64f(xy_a + ps * 768u + 256u), P3 = lds64f(xy_a + ps * 768u + 512u);
+        const float2 P1 = lds64f(xy_a + (ps << 8)), P2 = lds64f(xy_a + (ps << 8) + 1024u), P3 = lds64f(xy_a + (ps << 8) + 2048u);
         const float x1 = P1.x, y1 = P1.y, x2 = P2.x, y2 = P2.y, x3 = P3.x, y3 = P3.y;
 
         // ---- phase A: bounds (Triangle::aabb, rasterizer.rs:58-66) ----------------------------
@@ -411,7 +412,9 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
             const bool cand = live && regular && !back;
             const uint32_t rows = maxy - miny, span = maxx - minx;
             // tight width <= 2  <=>  span <= 2 or floor(max_x) <= minx + 1   (see tight_width)
-            const bool foot = cand && rows <= 2u && (span <= 2u || __float2uint_rz(floorf(mx0)) <= minx + 1u);   // tier 1
+            // (span <= 3: a triangle at the left edge of the screen; tier 2 takes those, so that the footprint's three columns
+            // are always inside the scan domain and column 2 always decides whether the row is finished)
+            const bool foot = cand && rows <= 2u && span > 3u && __float2uint_rz(floorf(mx0)) <= minx + 1u;   // tier 1
             bool beyond = cand && !foot;   // tier 2 / 3: handled in the rare block
 
             // ---- tier 1: 2 x 3 footprint in registers, lockstep (same evaluation as k_geom3) ------------
@@ -441,11 +444,10 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
                 cov_test<8>(cov, cr[1][0], gc[0][0], cr[1][1], gc[0][1], cr[1][2], gc[0][2]);
                 cov_test<16>(cov, cr[1][0], gc[1][0], cr[1][1], gc[1][1], cr[1][2], gc[1][2]);
                 cov_test<32>(cov, cr[1][0], gc[2][0], cr[1][1], gc[2][1], cr[1][2], gc[2][2]);
-                const uint32_t cm = (1u << min(span, 3u)) - 1u;
-                const uint32_t valid = cm | (rows > 1u ? cm << 3 : 0u);
+                const uint32_t valid = rows > 1u ? 63u : 7u;
                 // a row is finished after column 2 if a closing edge (dy >= 0) fails there
                 bool open = false;
-                if (span > 3u) {
+                {
                     const bool nd0 = !(dy0 < 0.0f), nd1 = !(dy1 < 0.0f), nd2 = !(dy2 < 0.0f);
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
