@@ -384,6 +384,7 @@ bool bounded_frame(const sloth_ctx* c, const FrameParams& p)
 }
 
 // whole-frame, bounded: super-chunks certified back-facing for this frame's matrix are taken off k_tri's list
+static constexpr size_t LIVE_SLACK = 65536;   // >= 4 * (warps of the largest k_tri grid: 148 SMs x 4 blocks x 16 warps)
 bool cone_frame(const sloth_ctx* c, const FrameParams& p) { return c->row1 == 0 && !c->tri_pairs && p.cone_on && bounded_frame(c, p); }
 
 // Everything of the indexed path that can run ahead of k_tri, into frame-state set `set` on stream `st`: Triangle::mul
@@ -929,10 +930,20 @@ int build_index(sloth_ctx* c, size_t n_tri)
         if (c->n_super) {
             CU_IX(cudaMalloc(&c->sc_super, (size_t)c->n_super * sizeof(ix::SuperChunk)));
             CU_IX(cudaMalloc(&c->sc_super_ids, (size_t)c->n_super * ix::SC_IDS * sizeof(uint32_t)));
-            for (int i = 0; i < 2; ++i) CU_IX(cudaMalloc(&c->live_sc[i], (size_t)c->n_super * sizeof(uint32_t)));
+            // k_tri<CONE>'s flat work list: the chunks behind the last full super-chunk come first and never change
+            const uint32_t n_chunks_all = (uint32_t)((n_tri + 31) / 32), tail_first = c->n_super * ix::SC_CHUNKS;
+            std::vector<uint32_t> tail(n_chunks_all - tail_first);
+            for (size_t i = 0; i < tail.size(); ++i) tail[i] = tail_first + (uint32_t)i;
+            for (int i = 0; i < 2; ++i) {
+                // + room for k_tri's look-ahead past the end of the list (4 iterations of every resident warp), zeroed:
+                // every entry is a valid chunk index at all times
+                CU_IX(cudaMalloc(&c->live_sc[i], ((size_t)n_chunks_all + LIVE_SLACK) * sizeof(uint32_t)));
+                CU_IX(cudaMemset(c->live_sc[i], 0, ((size_t)n_chunks_all + LIVE_SLACK) * sizeof(uint32_t)));
+                if (!tail.empty()) CU_IX(cudaMemcpy(c->live_sc[i], tail.data(), tail.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            }
             for (int i = 0; i < 2; ++i) CU_IX(cudaMalloc(&c->skip_sc[i], (size_t)c->n_super * sizeof(uint32_t)));
             for (int i = 0; i < 2; ++i) CU_IX(cudaMalloc(&c->cone_cnt[i], sizeof(ConeCounts)));
-            ix::k_ix_super<<<c->n_super, 256, 0, c->stream>>>(c->sc_rec, px, px + c->pos_stride, px + 2 * c->pos_stride, c->sc_super,
+            ix::k_ix_super<<<c->n_super, ix::SC_TRIS, 0, c->stream>>>(c->sc_rec, px, px + c->pos_stride, px + 2 * c->pos_stride, c->sc_super,
                                                               c->sc_super_ids);
             c->launches += 1;
         }

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) k_ix_connectivity(uint4* __restrict__ rec
 }
 
 // ---------------------------------------------------------------------------------
-// Super-chunks: 8 consecutive chunks = 256 triangles.  Per super-chunk, once per scene:
+// Super-chunks: SC_CHUNKS consecutive chunks (8 = 256 triangles by default).  Per super-chunk, once per scene:
 //   * the cone of its triangles' object-space normals n_t = (V1-V3) x (V2-V1) (axis, half-angle), the smallest |n_t|
 //     and the longest edge -- the rotation-independent half of the certificate "every triangle of this super-chunk
 //     is back-facing by a margin" that k_super_pass (tri_kernel.cuh) completes per frame;
@@ -246,9 +246,15 @@ __global__ void __launch_bounds__(256) k_ix_connectivity(uint4* __restrict__ rec
 // 60 degrees, it has at most SC_IDS unique vertices, and every triangle but the first shares a vertex with an earlier
 // one (then the row ranges of its triangles form one interval, see k_ix_connectivity).  One block per super-chunk.
 // ---------------------------------------------------------------------------------
-static constexpr uint32_t SC_CHUNKS = 8;
+#ifndef SLOTH_SC_CHUNKS
+#define SLOTH_SC_CHUNKS 8      // chunks of 32 triangles per super-chunk: 2, 4 or 8
+#endif
+static constexpr uint32_t SC_CHUNKS = SLOTH_SC_CHUNKS;
 static constexpr uint32_t SC_TRIS = SC_CHUNKS * 32u;
-static constexpr uint32_t SC_IDS = 384;          // 12 per lane of the warp that reads them
+static constexpr uint32_t SC_WARPS = SC_CHUNKS;  // k_ix_super: one thread per triangle
+static constexpr uint32_t SC_IDS = SC_TRIS + SC_TRIS / 2u;   // room for 1.5 unique vertices per triangle; 12 (6, 3) per lane of the warp
+                                                              // that reads them
+static constexpr uint32_t SC_SORT = 4u * SC_TRIS;             // 3 keys per triangle, padded to a power of two
 
 struct SuperChunk {        // 32 bytes
     float ax, ay, az;      // unit cone axis times cos(half-angle)      (half-angle rounded up)
@@ -258,7 +264,7 @@ struct SuperChunk {        // 32 bytes
     uint32_t n_ids, pad;
 };
 
-__device__ __forceinline__ double block_reduce(double v, int op, double* s_part)   // op 0 sum, 1 min, 2 max; 256 threads
+__device__ __forceinline__ double block_reduce(double v, int op, double* s_part)   // op 0 sum, 1 min, 2 max; SC_WARPS warps
 {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -269,29 +275,29 @@ __device__ __forceinline__ double block_reduce(double v, int op, double* s_part)
     if ((threadIdx.x & 31u) == 0) s_part[threadIdx.x >> 5] = v;
     __syncthreads();
     double r = s_part[0];
-    for (int w = 1; w < 8; ++w) r = op == 0 ? r + s_part[w] : (op == 1 ? fmin(r, s_part[w]) : fmax(r, s_part[w]));
+    for (uint32_t w = 1; w < SC_WARPS; ++w) r = op == 0 ? r + s_part[w] : (op == 1 ? fmin(r, s_part[w]) : fmax(r, s_part[w]));
     return r;
 }
 
-__global__ void __launch_bounds__(256) k_ix_super(const uint4* __restrict__ rec, const float* __restrict__ px,
-                                                  const float* __restrict__ py, const float* __restrict__ pz,
-                                                  SuperChunk* __restrict__ out, uint32_t* __restrict__ ids)
+__global__ void __launch_bounds__(SC_TRIS) k_ix_super(const uint4* __restrict__ rec, const float* __restrict__ px,
+                                                      const float* __restrict__ py, const float* __restrict__ pz,
+                                                      SuperChunk* __restrict__ out, uint32_t* __restrict__ ids)
 {
-    __shared__ unsigned long long s_key[1024];
-    __shared__ double s_part[8];
-    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_key[SC_SORT];
+    __shared__ double s_part[SC_WARPS];
+    __shared__ uint32_t s_warp[SC_WARPS];
     __shared__ int s_fail;
     const uint32_t sc = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint4 r = rec[(size_t)sc * SC_TRIS + tid];
     const uint32_t id[3] = {r.x, r.y, r.z};
 #pragma unroll
     for (int j = 0; j < 3; ++j) s_key[tid * 3u + j] = ((unsigned long long)id[j] << 32) | tid;
-    s_key[768u + tid] = ~0ull;
+    s_key[3u * SC_TRIS + tid] = ~0ull;
     if (tid == 0) s_fail = 0;
     __syncthreads();
-    for (uint32_t k = 2; k <= 1024u; k <<= 1)      // bitonic sort of (vertex id, triangle) pairs
+    for (uint32_t k = 2; k <= SC_SORT; k <<= 1)      // bitonic sort of (vertex id, triangle) pairs
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = tid; i < 1024u; i += 256u) {
+            for (uint32_t i = tid; i < SC_SORT; i += SC_TRIS) {
                 const uint32_t x = i ^ j;
                 if (x > i) {
                     const unsigned long long a = s_key[i], b = s_key[x];
@@ -317,7 +323,7 @@ __global__ void __launch_bounds__(256) k_ix_super(const uint4* __restrict__ rec,
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     uint32_t off = incl - mine, n_ids = 0;
-    for (uint32_t w = 0; w < 8u; ++w) {
+    for (uint32_t w = 0; w < SC_WARPS; ++w) {
         if (w < warp) off += s_warp[w];
         n_ids += s_warp[w];
     }
@@ -329,13 +335,13 @@ __global__ void __launch_bounds__(256) k_ix_super(const uint4* __restrict__ rec,
             ++off;
         }
     const uint32_t id0 = (uint32_t)(s_key[0] >> 32);
-    for (uint32_t i = n_ids + tid; i < SC_IDS; i += 256u) my_ids[i] = id0;   // padding: a vertex that is in the list anyway
+    for (uint32_t i = n_ids + tid; i < SC_IDS; i += SC_TRIS) my_ids[i] = id0;   // padding: a vertex that is in the list anyway
     // every triangle but the first shares a vertex with an earlier one (smallest triangle index per id = the low
     // word of the id's first sorted pair)
     bool linked = tid == 0u;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        uint32_t lo = 0, hi = 768u;
+        uint32_t lo = 0, hi = 3u * SC_TRIS;
         const unsigned long long want = (unsigned long long)id[j] << 32;
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;

@@ -30,7 +30,7 @@ struct FrameAux {
 
 // Lengths of the two super-chunk lists of a frame (k_super_cert); cleared on the transform stream, apart from FrameAux.
 struct ConeCounts {
-    uint32_t n_live;   // entries of Queues::live_sc: super-chunks left for k_tri
+    uint32_t n_live;   // super-chunks left for k_tri (Queues::live_sc holds SC_CHUNKS chunk indices for each)
     uint32_t n_skip;   // entries of Queues::skip_sc: certified back-facing, only their row stamps remain
 };
 
@@ -42,7 +42,8 @@ struct Queues {
     // '\n' marker (rasterizer.rs:89-91), 0 = row never stamped.  [H + 64]
     uint32_t* __restrict__ rowmax;
     FrameAux* __restrict__ aux;
-    uint32_t* __restrict__ live_sc;              // [super-chunks] the ones k_super_cert could not certify as back-facing
+    uint32_t* __restrict__ live_sc;              // [chunks] k_tri<CONE>'s work list: the chunks behind the last full super-chunk
+                                                 // (static), then SC_CHUNKS entries per super-chunk k_super_cert could not certify
     uint32_t* __restrict__ skip_sc;              // [super-chunks] the certified ones: only their row stamps remain
     ConeCounts* __restrict__ cone_cnt;
 };

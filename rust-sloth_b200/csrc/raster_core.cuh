@@ -210,6 +210,9 @@ SLOTH_DEV uint32_t glyph_index(const FrameParams& p, float shade)
 // (rasterizer.rs:81): smaller z wins; equal z -> smaller triangle index; same
 // triangle hitting one id twice (row wrap) -> the wrapped fragment of row y-1
 // precedes the direct fragment of row y.
+// LEAN (k_tri's whole-frame instantiations): the context owns all rows, so krow0 = 0, and the SLOTH_DEBUG bit that
+// skips the atomic is not looked at.
+template <bool LEAN = false>
 SLOTH_DEV void emit_fragment(const FrameParams& p, const Setup& s, const Shade& sh, uint32_t tri, uint32_t x,
                              uint32_t y, float w0, float w1, float w2, unsigned long long* __restrict__ keys)
 {
@@ -218,7 +221,7 @@ SLOTH_DEV void emit_fragment(const FrameParams& p, const Setup& s, const Shade& 
     const uint32_t kx = x * p.XS;
     const uint32_t direct = kx < p.KW ? 1u : 0u;
     const uint32_t row = y + 1u - direct;
-    if (row < p.krow0 || row >= p.row1) return;
+    if ((!LEAN && row < p.krow0) || row >= p.row1) return;
     const float shade = mul(sh.k, add(add(w0, w1), w2));
     const uint32_t g = glyph_index(p, shade);
     uint32_t zb = __float_as_uint(z);
@@ -226,8 +229,8 @@ SLOTH_DEV void emit_fragment(const FrameParams& p, const Setup& s, const Shade& 
     const uint32_t ord = (zb & 0x80000000u) ? ~zb : (zb | 0x80000000u);
     const unsigned long long key =
         ((unsigned long long)ord << 32) | (unsigned long long)((tri << 5) | (direct << 4) | g);
-    const uint32_t L = y * p.KW + kx - p.krow0 * p.KW;
-    if (!(p.debug & 1u)) atomicMin(keys + L, key);
+    const uint32_t L = LEAN ? y * p.KW + kx : y * p.KW + kx - p.krow0 * p.KW;
+    if (LEAN || !(p.debug & 1u)) atomicMin(keys + L, key);
 }
 
 // Number of rows one row-band work item of the walk kernel covers.

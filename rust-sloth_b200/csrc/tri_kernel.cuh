@@ -116,7 +116,8 @@ SLOTH_DEV void cov_test(uint32_t& cov, float a0, float b0, float a1, float b1, f
         : "f"(a0), "f"(b0), "f"(a1), "f"(b1), "f"(a2), "f"(b2), "n"(BIT));
 }
 
-// Emit `count` parked fragments starting at ring position `head`, lane = fragment.
+// Emit `count` parked fragments starting at ring position `head`, lane = fragment.  LEAN: whole-frame context.
+template <bool LEAN = false>
 SLOTH_DEV void t_emit(const FrameParams& p, const Scene& sc, const TRing& wq, uint32_t head, uint32_t count, uint32_t lane,
                       unsigned long long* __restrict__ keys)
 {
@@ -140,7 +141,7 @@ SLOTH_DEV void t_emit(const FrameParams& p, const Scene& sc, const TRing& wq, ui
     const RowC rc = row_setup(s, y);
     float w0, w1, w2;
     edge_eval(s, rc, x, w0, w1, w2);
-    emit_fragment(p, s, sh, tri, x, y, w0, w1, w2, keys);
+    emit_fragment<LEAN>(p, s, sh, tri, x, y, w0, w1, w2, keys);
 }
 
 // ---------------------------------------------------------------------------------
@@ -197,8 +198,16 @@ __global__ void __launch_bounds__(256) k_super_cert(const __grid_constant__ Fram
     base_live = __shfl_sync(0xFFFFFFFFu, base_live, 0);
     base_skip = __shfl_sync(0xFFFFFFFFu, base_skip, 0);
     const unsigned below = (1u << lane) - 1u;
-    if (skip) q.skip_sc[base_skip + __popc(m_skip & below)] = sc;
-    else if (sc < n_sc) q.live_sc[base_live + __popc(m_live & below)] = sc;
+    if (skip) {
+        q.skip_sc[base_skip + __popc(m_skip & below)] = sc;
+    } else if (sc < n_sc) {
+        // k_tri's work list is flat: one entry per chunk.  It starts with the chunks behind the last full super-chunk
+        // (written once, when the scene is set), the chunks of the live super-chunks follow.
+        const uint32_t n_tail = ((p.n_tri + 31u) >> 5) - p.cone_n_super * ix::SC_CHUNKS;
+        uint32_t* out = q.live_sc + n_tail + (base_live + __popc(m_live & below)) * ix::SC_CHUNKS;
+#pragma unroll
+        for (uint32_t j = 0; j < ix::SC_CHUNKS; ++j) out[j] = sc * ix::SC_CHUNKS + j;
+    }
 }
 
 // Row range [lo, hi) a certified super-chunk stamps (image mode), by one warp: min / max of y' over its vertex list.
@@ -282,10 +291,9 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     // of k + 2 and k + 4 are one XOR away.  Band contexts keep `live`, a shift register over the next five
     // iterations (bit j <-> iteration k + j: not culled): only live chunks are copied, gathered and computed.
     // Past the end the record copies are clamped to the warp's last chunk (valid memory, results unused).
-    // CONE: work item i = (live super-chunk i / 8, chunk i % 8 of it); the chunks behind the last full super-chunk follow
-    const uint32_t n_sc_items = CONE ? q.cone_cnt->n_live * ix::SC_CHUNKS : 0u;
-    const uint32_t tail_first = CONE ? p.cone_n_super * ix::SC_CHUNKS : 0u;
-    const uint32_t n_items = CONE ? n_sc_items + (n_chunks - tail_first) : n_chunks;
+    // CONE: work item i = entry i of the flat chunk list k_super_cert left (the chunks behind the last full super-chunk,
+    // then the chunks of the super-chunks it could not certify)
+    const uint32_t n_items = CONE ? (n_chunks - p.cone_n_super * ix::SC_CHUNKS) + q.cone_cnt->n_live * ix::SC_CHUNKS : n_chunks;
     const uint32_t n_iter = gw < n_items ? (n_items - gw + n_warps - 1u) / n_warps : 0u;
     uint32_t rec_a = smem_u32(&ws.pipe.rec[0][lane]), xy_a = smem_u32(&ws.pipe.xy[0][0][lane]);
     uint32_t ring_a = smem_u32(&wq.rec[0]);   // wq.xy follows at + 16 * T_RING
@@ -296,27 +304,18 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
         if (!BAND) return 1u;
         return (k < n_iter && !culled(gw + k * n_warps)) ? 1u : 0u;
     };
-    // CONE: lane l keeps the chunk of iteration cb + l (and of cb + 32 + l, loaded one block of 32 iterations ahead of
-    // its first use).  The chunk index is only needed to fetch the record: the record names its own triangle.
-    uint32_t cb = 0, c_blk = 0, c_blk_next = 0;
-    auto chunk_of_iter = [&](uint32_t j) -> uint32_t {   // chunk of this warp's iteration j (clamped to its last one)
-        const uint32_t i = gw + min(j, n_iter - 1u) * n_warps;
-        return i < n_sc_items ? __ldg(q.live_sc + (i >> 3)) * ix::SC_CHUNKS + (i & (ix::SC_CHUNKS - 1u)) : tail_first + (i - n_sc_items);
+    // CONE: the chunk index is only needed to fetch the record (the record names its own triangle): one broadcast load
+    // from the list, issued at the top of the iteration that ends with the fetch.  The list is allocated with room for
+    // the look-ahead past its end and only ever holds valid chunk indices (zeroed at allocation), so the walk needs no
+    // clamp: what it fetches past the end is never used.
+    uint32_t li = gw;   // list entry of the next chunk index to load
+    auto next_chunk = [&]() -> uint32_t {
+        const uint32_t c = __ldg(q.live_sc + li);
+        li += n_warps;
+        return c;
     };
-    auto chunk_lookup = [&](uint32_t j) -> uint32_t {    // j ascends by one from call to call
-        if (j - cb >= 32u) {
-            cb += 32u;
-            c_blk = c_blk_next;
-            c_blk_next = chunk_of_iter(cb + 32u + lane);
-        }
-        return __shfl_sync(0xFFFFFFFFu, c_blk, j - cb);
-    };
-    if (CONE && n_iter) {
-        c_blk = chunk_of_iter(lane);
-        c_blk_next = chunk_of_iter(32u + lane);
-    }
-    auto fetch_rec = [&](uint32_t k, uint32_t slot) {   // record of iteration k -> ring slot (k ascends by one from call to call)
-        if (CONE) cp_async16(rec_a + (slot << 9), sc.rec + (size_t)chunk_lookup(k) * 32u + lane);
+    auto fetch_rec = [&](uint32_t k, uint32_t slot) {   // record of iteration k -> ring slot (CONE: k ascends by one per call)
+        if (CONE) cp_async16(rec_a + (slot << 9), sc.rec + (size_t)next_chunk() * 32u + lane);
         else cp_async16(rec_a + (slot << 9), rec_g + (size_t)min(k, n_iter - 1u) * rec_step);
     };
     auto gather_xy = [&](uint32_t slot) {   // (x', y') of the three corners of the record in ring slot `slot`
@@ -342,6 +341,8 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
 
     for (uint32_t k = 0; k < n_iter; ++k) {
         const uint32_t ps = k & 3u;   // ring slot of this iteration's record and coordinates
+        uint32_t c_next = 0;
+        if (CONE) c_next = next_chunk();   // chunk of iteration k + 4: in flight during this one, used by the fetch at its end
         cp_async_wait<1>();   // everything committed two iterations ago has landed: coordinates k, record k + 2
         if (!BAND || (live & 4u)) gather_xy(ps ^ 2u);
         uint32_t mask = 0, minx = 0, miny = 0;
@@ -507,7 +508,7 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
                     q_tail += __popc(who);
                     if (q_tail >= q_lim) {
                         __syncwarp();
-                        t_emit(p, sc, wq, q_lim - 32u, 32u, lane, keys);
+                        t_emit<!BAND && !SLOTH_TRI_KNOBS>(p, sc, wq, q_lim - 32u, 32u, lane, keys);
                         __syncwarp();
                         q_lim += 32u;
                     }
@@ -569,7 +570,7 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
                 q_tail += __popc(who);
                 if (q_tail >= q_lim) {
                     __syncwarp();
-                    t_emit(p, sc, wq, q_lim - 32u, 32u, lane, keys);
+                    t_emit<!BAND && !SLOTH_TRI_KNOBS>(p, sc, wq, q_lim - 32u, 32u, lane, keys);
                     __syncwarp();
                     q_lim += 32u;
                 }
@@ -583,6 +584,8 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
             const uint32_t l = is_live(k + 4u);
             live = (live >> 1) | (l << 3);
             if (l) fetch_rec(k + 4u, ps);
+        } else if (CONE) {
+            cp_async16(rec_a + (ps << 9), sc.rec + (size_t)c_next * 32u + lane);
         } else {
             fetch_rec(k + 4u, ps);
         }
@@ -592,7 +595,7 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     if (!BAND) chunks_done = n_iter;
     if (q_tail != q_lim - 32u) {
         __syncwarp();
-        t_emit(p, sc, wq, q_lim - 32u, q_tail - (q_lim - 32u), lane, keys);
+        t_emit<!BAND && !SLOTH_TRI_KNOBS>(p, sc, wq, q_lim - 32u, q_tail - (q_lim - 32u), lane, keys);
     }
     if (ROWMAX_SHARED && do_stamps) {   // publish this block's stamps (the probe skips most atomics)
         __syncthreads();
