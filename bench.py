@@ -374,6 +374,8 @@ def run_b200(args, rank, local_rank, world):
             tj = json.load(open(tpath))
             traffic = tj.get(f"{kernel_name}_dram_bytes_per_launch")
             traffic_src = f"{tj.get('capture', 'ncu --set full')} at commit {tj.get('commit', '?')}"
+        r_ms = float(np.mean(resolve_ms))
+        r_traffic = json.load(open(tpath)).get("k_resolve_even_dram_bytes_per_launch") if os.path.exists(tpath) else None
         fps = K * world / (dev_ms_max * 1e-3)
         e2e_fps = K * world / (e2e_ms_max * 1e-3)
         e2e_cells_fps = K * world / (e2e_cells_ms_max * 1e-3)
@@ -410,6 +412,13 @@ def run_b200(args, rank, local_rank, world):
                                        "k_resolve": float(np.mean(resolve_ms)),
                                        "frame_unoverlapped": float(np.mean(frame_ms))},
                          "geometry_path": "indexed" if indexed else "soup", "unique_vertices": int(last["n_vert"])},
+            # the write-out kernel against the same peak: 4 bytes per cell are its algorithmic bytes; what it actually
+            # moves is the 8-byte key per slot in (and back out where a fragment landed) plus the cells
+            "roofline_resolve": {"bound": "hbm", "kernel": "k_resolve_even", "achieved": 4.0 * WIDTH * HEIGHT / (r_ms * 1e-3) / 1e9,
+                                 "peak": hbm_peak, "unit": "GB/s", "frac": 4.0 * WIDTH * HEIGHT / (r_ms * 1e-3) / 1e9 / hbm_peak,
+                                 "algorithmic_bytes_per_launch": 4 * WIDTH * HEIGHT, "avg_launch_ms": r_ms,
+                                 "traffic": r_traffic, "traffic_frac": (r_traffic / (r_ms * 1e-3) / 1e9 / hbm_peak) if r_traffic else None,
+                                 "traffic_source": traffic_src},
             "post_check": post_check,
             "gpu_launches": int(launches_timed),
             "clocks": clk.summary(t_wall0, t_wall1),

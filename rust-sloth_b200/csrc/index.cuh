@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) k_ix_connectivity(uint4* __restrict__ rec
 }
 
 // ---------------------------------------------------------------------------------
-// Super-chunks: SC_CHUNKS consecutive chunks (8 = 256 triangles by default).  Per super-chunk, once per scene:
+// Super-chunks: SC_CHUNKS consecutive chunks (4 = 128 triangles by default).  Per super-chunk, once per scene:
 //   * the cone of its triangles' object-space normals n_t = (V1-V3) x (V2-V1) (axis, half-angle), the smallest |n_t|
 //     and the longest edge -- the rotation-independent half of the certificate "every triangle of this super-chunk
 //     is back-facing by a margin" that k_super_pass (tri_kernel.cuh) completes per frame;
@@ -246,8 +246,12 @@ __global__ void __launch_bounds__(256) k_ix_connectivity(uint4* __restrict__ rec
 // 60 degrees, it has at most SC_IDS unique vertices, and every triangle but the first shares a vertex with an earlier
 // one (then the row ranges of its triangles form one interval, see k_ix_connectivity).  One block per super-chunk.
 // ---------------------------------------------------------------------------------
+// Size of a super-chunk in chunks of 32 triangles: 2, 4 or 8.  Smaller super-chunks have narrower normal cones and
+// reach closer to the silhouette (bench workload, k_tri alone: 102.3 us with 8, 97.9 us with 4, 95.0 us with 2), but
+// every certified one costs k_super_stamp a latency chain (23 / 28 / 54 us of k_tail + k_super_stamp): 4 is the best
+// frame.  (profiles/r02/r02_superchunk_size_ab.log)
 #ifndef SLOTH_SC_CHUNKS
-#define SLOTH_SC_CHUNKS 8      // chunks of 32 triangles per super-chunk: 2, 4 or 8
+#define SLOTH_SC_CHUNKS 4
 #endif
 static constexpr uint32_t SC_CHUNKS = SLOTH_SC_CHUNKS;
 static constexpr uint32_t SC_TRIS = SC_CHUNKS * 32u;

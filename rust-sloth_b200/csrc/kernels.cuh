@@ -682,7 +682,8 @@ __global__ void __launch_bounds__(256) k_resolve_even(const __grid_constant__ Fr
         key[m] = KEY_EMPTY;
         if (i < n_slots) {
             key[m] = keys[i];
-            keys[i] = KEY_EMPTY;   // the key plane is clean again for the next frame
+            if (key[m] != KEY_EMPTY) keys[i] = KEY_EMPTY;   // the key plane is clean again for the next frame (sectors
+                                                            // without a fragment are not written at all)
         }
     }
     uint32_t c0[RESOLVE_SLOTS], c1[RESOLVE_SLOTS];

@@ -210,36 +210,44 @@ __global__ void __launch_bounds__(256) k_super_cert(const __grid_constant__ Fram
     }
 }
 
-// Row range [lo, hi) a certified super-chunk stamps (image mode), by one warp: min / max of y' over its vertex list.
-SLOTH_DEV void super_rows(const FrameParams& p, const uint32_t* __restrict__ ids, const float2* __restrict__ vxy, uint32_t sc,
-                          uint32_t lane, uint32_t& lo, uint32_t& hi)
-{
-    const uint32_t* my = ids + (size_t)sc * ix::SC_IDS;
-    float y[ix::SC_IDS / 32];
-#pragma unroll
-    for (uint32_t j = 0; j < ix::SC_IDS / 32; ++j) y[j] = __ldg(&vxy[__ldg(my + j * 32u + lane)].y);
-    float mn = y[0], mx = y[0];
-#pragma unroll
-    for (uint32_t j = 1; j < ix::SC_IDS / 32; ++j) { mn = fminf(mn, y[j]); mx = fmaxf(mx, y[j]); }
-    lo = __reduce_min_sync(0xFFFFFFFFu, __float2uint_rz(ceilf(fmaxf(mn, 1.0f))));
-    hi = __reduce_max_sync(0xFFFFFFFFu, __float2uint_rz(ceilf(fminf(mx, p.hm1))));
-}
-
-// k_super_stamp (image mode, after k_tri, before the resolve of the same frame): one warp per entry of the skip list,
-// taken from the end -- the list is roughly ascending, so the highest indices reach a row first and most later
-// entries find it stamped already (one load instead of an atomic on a contended word).
+// k_super_stamp (image mode, after k_tri, before the resolve of the same frame): the rows [lo, hi) a certified
+// super-chunk stamps are the min / max of y' over its vertex list.  One warp takes E entries of the skip list per turn
+// (E x SC_IDS = 384 ids, 12 per lane) and issues each level of the dependent chain -- list entry, vertex ids, y' -- for
+// all of them before it waits: the kernel is nothing but memory latency.  The list is walked from the end: it is
+// roughly ascending, so the highest indices reach a row first and most later entries find it stamped already (one load
+// instead of an atomic on a contended word).
 __global__ void __launch_bounds__(128) k_super_stamp(const __grid_constant__ FrameParams p, const uint32_t* __restrict__ ids,
                                                      const float2* __restrict__ vxy, const Queues q)
 {
+    constexpr uint32_t E = 8u / ix::SC_CHUNKS, J = ix::SC_IDS / 32u;
     const uint32_t lane = threadIdx.x & 31u, wpb = blockDim.x >> 5;
     const uint32_t n_skip = q.cone_cnt->n_skip, n_warps = gridDim.x * wpb;
-    for (uint32_t i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n_skip; i += n_warps) {
-        const uint32_t s_c = q.skip_sc[n_skip - 1u - i];
-        uint32_t lo, hi;
-        super_rows(p, ids, vxy, s_c, lane, lo, hi);
-        const uint32_t value = s_c * ix::SC_CHUNKS + ix::SC_CHUNKS;   // 1 + index of its last chunk
-        for (uint32_t r = lo + lane; r < hi; r += 32u)
-            if (__ldcg(q.rowmax + r) < value) atomicMax(q.rowmax + r, value);
+    for (uint32_t i = (blockIdx.x * wpb + (threadIdx.x >> 5)) * E; i < n_skip; i += n_warps * E) {
+        uint32_t s_c[E], id[E][J];
+        float y[E][J];
+#pragma unroll
+        for (uint32_t e = 0; e < E; ++e) s_c[e] = q.skip_sc[n_skip - 1u - min(i + e, n_skip - 1u)];   // past the end: the last entry again
+#pragma unroll
+        for (uint32_t e = 0; e < E; ++e)
+#pragma unroll
+            for (uint32_t j = 0; j < J; ++j) id[e][j] = __ldg(ids + (size_t)s_c[e] * ix::SC_IDS + j * 32u + lane);
+#pragma unroll
+        for (uint32_t e = 0; e < E; ++e)
+#pragma unroll
+            for (uint32_t j = 0; j < J; ++j) y[e][j] = __ldg(&vxy[id[e][j]].y);
+#pragma unroll
+        for (uint32_t e = 0; e < E; ++e) {
+            if (e && i + e >= n_skip) break;   // warp-uniform
+            float mn = y[e][0], mx = y[e][0];
+#pragma unroll
+            for (uint32_t j = 1; j < J; ++j) { mn = fminf(mn, y[e][j]); mx = fmaxf(mx, y[e][j]); }
+            // ceil commutes with min / max: the same rows as the union of the triangles' own [miny, maxy)
+            const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, __float2uint_rz(ceilf(fmaxf(mn, 1.0f))));
+            const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, __float2uint_rz(ceilf(fminf(mx, p.hm1))));
+            const uint32_t value = s_c[e] * ix::SC_CHUNKS + ix::SC_CHUNKS;   // 1 + index of its last chunk
+            for (uint32_t r = lo + lane; r < hi; r += 32u)
+                if (__ldcg(q.rowmax + r) < value) atomicMax(q.rowmax + r, value);
+        }
     }
 }
 
