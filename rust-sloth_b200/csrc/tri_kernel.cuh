@@ -278,6 +278,8 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     if (ROWMAX_SHARED && do_stamps)
         for (uint32_t i = threadIdx.x; i < n_rowmax; i += blockDim.x) s_rowmax[i] = 0u;
     __syncthreads();
+    uint32_t stamp_bit = do_stamps ? 1u : 0u;   // ANDed with the record's connected flag: one test per chunk for both
+    asm volatile("" : "+r"(stamp_bit));
     uint32_t rowmax_a = smem_u32(s_rowmax);
     asm volatile("" : "+r"(rowmax_a));   // keep the shared-window address in a register (the compiler would re-derive it
                                          // from the CTA id with an S2UR at every use)
@@ -316,10 +318,12 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     // from the list, issued at the top of the iteration that ends with the fetch.  The list is allocated with room for
     // the look-ahead past its end and only ever holds valid chunk indices (zeroed at allocation), so the walk needs no
     // clamp: what it fetches past the end is never used.
-    uint32_t li = gw;   // list entry of the next chunk index to load
+    const uint32_t* live_p = q.live_sc + gw;   // list entry of the next chunk index to load (a running pointer: no constant
+                                               // load and no index arithmetic per chunk)
+    const float2* const vxy_p = sc.vxy;
     auto next_chunk = [&]() -> uint32_t {
-        const uint32_t c = __ldg(q.live_sc + li);
-        li += n_warps;
+        const uint32_t c = __ldg(live_p);
+        live_p += n_warps;
         return c;
     };
     auto fetch_rec = [&](uint32_t k, uint32_t slot) {   // record of iteration k -> ring slot (CONE: k ascends by one per call)
@@ -328,9 +332,9 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
     };
     auto gather_xy = [&](uint32_t slot) {   // (x', y') of the three corners of the record in ring slot `slot`
         const uint4 r = lds128(rec_a + (slot << 9));
-        cp_async8(xy_a + (slot << 8), sc.vxy + r.x);
-        cp_async8(xy_a + (slot << 8) + 1024u, sc.vxy + r.y);
-        cp_async8(xy_a + (slot << 8) + 2048u, sc.vxy + r.z);
+        cp_async8(xy_a + (slot << 8), vxy_p + r.x);
+        cp_async8(xy_a + (slot << 8) + 1024u, vxy_p + r.y);
+        cp_async8(xy_a + (slot << 8) + 2048u, vxy_p + r.z);
     };
     uint32_t live = 0;
     if (n_iter) {
@@ -376,8 +380,8 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
         // A chunk whose 32 triangles hang together through shared vertices (flag in the record, set at scene-set)
         // stamps exactly the rows [min miny, max maxy): the y-ranges of triangles that share a vertex overlap or
         // touch, so the union of the chunk's ranges has no gap, and ceil() commutes with min / max.
-        const bool connected = !BAND && !CHECK_REGULAR && (rec_w & 1u) != 0u;   // warp-uniform
-        if (do_stamps && connected) {
+        const bool connected = !BAND && !CHECK_REGULAR && (rec_w & stamp_bit) != 0u;   // warp-uniform; implies do_stamps
+        if (connected) {
             const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, miny);
             const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, maxy);
             if (lo + lane < hi) stamp(lo + lane, c + 1u);
@@ -429,16 +433,17 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
             // ---- tier 1: 2 x 3 footprint in registers, lockstep (same evaluation as k_geom3) ------------
             if (__any_sync(0xFFFFFFFFu, foot)) {
                 float cr[2][3], gc[3][3];
+                const float fx0 = (float)minx, fy0 = (float)miny;   // < 2^16 where it matters: fx0 + k == (float)(minx + k) exactly
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
-                    const float py = (float)(miny + r);
+                    const float py = r ? add(fy0, 1.0f) : fy0;
                     cr[r][0] = mul(dx0, sub(py, y2));
                     cr[r][1] = mul(dx1, sub(py, y3));
                     cr[r][2] = mul(dx2, sub(py, y1));
                 }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const float px = (float)(minx + k);
+                    const float px = k ? add(fx0, (float)k) : fx0;
                     gc[k][0] = mul(dy0, sub(px, x2));
                     gc[k][1] = mul(dy1, sub(px, x3));
                     gc[k][2] = mul(dy2, sub(px, x1));
@@ -563,7 +568,8 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
         if (who) {
             const uint32_t xy0 = minx | (miny << 16);
             const uint4 r = lds128(rec_a + (ps << 9));
-            const unsigned below = (1u << lane) - 1u;
+            unsigned below = (1u << lane) - 1u;
+            asm volatile("" : "+r"(below));   // otherwise recomputed in every turn
             do {
                 const bool has = mask != 0u;
                 const uint32_t bit = (uint32_t)__ffs((int)mask) - 1u;   // row * 3 + column; garbage when !has, unused
