@@ -640,10 +640,9 @@ int enqueue_resolve(sloth_ctx* c, const FrameParams& p, int set, cudaStream_t st
     }
     if ((c->W & 1u) == 0) {
         const uint32_t n_slots = rows * p.KW;
-        // a warp owns 32 * RESOLVE_SLOTS consecutive slots
-        const uint32_t per_warp = 32u * RESOLVE_SLOTS;
-        const uint32_t n_threads = std::max<uint32_t>((n_slots + per_warp - 1) / per_warp * 32u, n_tail ? 32u : 0u);
-        if (n_threads) k_resolve_even<<<(n_threads + CO_THREADS - 1) / CO_THREADS, CO_THREADS, 0, st>>>(p, sc, c->keys[set], q, d_out, n_slots, n_tail);
+        // grid = (segments of a row, rows): a block owns RESOLVE_SEG consecutive slots of one row (kernels.cuh)
+        const dim3 grid(std::max<uint32_t>(1u, (p.KW + RESOLVE_SEG - 1) / RESOLVE_SEG), rows);
+        if (rows) k_resolve_even<<<grid, CO_THREADS, 0, st>>>(p, sc, c->keys[set], q, d_out, n_slots, n_tail);
         c->launches += 1;
     } else {
         const uint32_t n_cells = rows * c->W;

@@ -451,7 +451,11 @@ __global__ void __launch_bounds__(256) k_xform(const __grid_constant__ FramePara
             ox[k] = xform_row(p.m + 0, x[k], y[k], z[k]);
             oy[k] = xform_row(p.m + 4, x[k], y[k], z[k]);
             oz[k] = xform_row(p.m + 8, x[k], y[k], z[k]);
-            if (i + k >= n_vert) { ox[k] = oy[k] = -1.0e30f; oz[k] = 0.0f; }   // the sentinel (and the padding after it)
+        }
+        if (i + 4u > n_vert) {   // only the thread that holds the end of the array: the sentinel (and the padding after it)
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k)
+                if (i + k >= n_vert) { ox[k] = oy[k] = -1.0e30f; oz[k] = 0.0f; }
         }
         float4* oxy = reinterpret_cast<float4*>(vxy + i);
         oxy[0] = make_float4(ox[0], oy[0], ox[1], oy[1]);

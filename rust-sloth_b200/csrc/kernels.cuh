@@ -651,41 +651,44 @@ SLOTH_DEV bool stamp_beats_fragment(const FrameParams& p, const Scene& sc, const
     return newline;
 }
 
-// W even: ids are even, one key slot owns cells (2k, 2k+1) of its row.  Four slots per thread, 32 apart (every
-// access of a warp is one contiguous 256-byte run): the key -> colour gather is a dependent load chain, so each
-// thread keeps four of them in flight -- the kernel usually runs as one block per SM beside the next frame's
-// geometry kernel, where only instruction-level parallelism hides the latency.  Row / column of a slot cost one
-// division per thread instead of one per slot; the newline-order check (warp-cooperative) is only entered when
-// some lane of the warp has a contested cell.
+// W even: ids are even, one key slot owns cells (2k, 2k+1) of its row.  The grid is (segments of a row, rows): a block
+// takes RESOLVE_SEG consecutive slots of ONE row, a warp 32 * RESOLVE_SLOTS of them, a thread RESOLVE_SLOTS slots 32
+// apart (every access of a warp is one contiguous 256-byte run).  Row and column come from the block index: no
+// division, and the newline stamp of the row (its cell (row, 1), owned by the slot at column 0) concerns exactly one
+// warp of the row's first block -- everybody else runs the bare key -> cell path.  The key -> colour gather is a
+// dependent load chain, so each thread keeps RESOLVE_SLOTS of them in flight: the kernel usually runs beside the next
+// frame's triangle kernel, where only instruction-level parallelism hides the latency, and every instruction it
+// issues there is one the triangle kernel does not.
 #ifndef RESOLVE_SLOTS_PER_THREAD
 #define RESOLVE_SLOTS_PER_THREAD 4
 #endif
 static constexpr uint32_t RESOLVE_SLOTS = RESOLVE_SLOTS_PER_THREAD;   // per thread
 // threads per block of the kernels that run beside the triangle kernel of a neighbouring frame (k_xform, k_resolve_even):
-// what is left of an SM next to three k_tri blocks is 10 K registers
+// what is left of an SM next to three k_tri blocks is 16 K registers
 #ifndef CO_THREADS
 #define CO_THREADS 128
 #endif
+static constexpr uint32_t RESOLVE_SEG = CO_THREADS * RESOLVE_SLOTS;   // slots of a row per block
 
-__global__ void __launch_bounds__(256) k_resolve_even(const __grid_constant__ FrameParams p, const Scene sc,
-                                                      unsigned long long* __restrict__ keys, const Queues q,
-                                                      uint32_t* __restrict__ cells, uint32_t n_slots,
-                                                      uint32_t n_tail)
+__global__ void __launch_bounds__(CO_THREADS) k_resolve_even(const __grid_constant__ FrameParams p, const Scene sc,
+                                                             unsigned long long* __restrict__ keys, const Queues q,
+                                                             uint32_t* __restrict__ cells, uint32_t n_slots,
+                                                             uint32_t n_tail)
 {
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t i0 = (tid >> 5) * (32u * RESOLVE_SLOTS) + (tid & 31u);   // this thread's slots: i0 + 32 m
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t row_local = blockIdx.y;                                            // row of the key plane / cell buffer
+    const uint32_t col0 = blockIdx.x * RESOLVE_SEG + warp * (32u * RESOLVE_SLOTS) + lane;   // this thread's columns: col0 + 32 m
+    const uint32_t i0 = row_local * p.KW + col0;
     const uint32_t blank = (uint32_t)' ';
     unsigned long long key[RESOLVE_SLOTS];
 #pragma unroll
-    for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m) {
-        const uint32_t i = i0 + 32u * m;
+    for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m) {   // all loads first: nothing between them that waits for one of them
         key[m] = KEY_EMPTY;
-        if (i < n_slots) {
-            key[m] = keys[i];
-            if (key[m] != KEY_EMPTY) keys[i] = KEY_EMPTY;   // the key plane is clean again for the next frame (sectors
-                                                            // without a fragment are not written at all)
-        }
+        if (col0 + 32u * m < p.KW) key[m] = __ldcs(keys + i0 + 32u * m);
     }
+#pragma unroll
+    for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m)     // the key plane is clean again for the next frame (sectors without a
+        if (key[m] != KEY_EMPTY) keys[i0 + 32u * m] = KEY_EMPTY;   // fragment are not written at all)
     uint32_t c0[RESOLVE_SLOTS], c1[RESOLVE_SLOTS];
 #pragma unroll
     for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m) {
@@ -693,41 +696,24 @@ __global__ void __launch_bounds__(256) k_resolve_even(const __grid_constant__ Fr
         if (key[m] != KEY_EMPTY) c0[m] = cell_of(p, sc, key[m]);
         c1[m] = c0[m];
     }
-    if (p.image) {   // warp-uniform
-        // the slot at column 0 of a row owns cells (row,0),(row,1); cell (row,1) is where the row's stamp goes
-        uint32_t row = 0, col = 0;
-        if (i0 < n_slots) { row = i0 / p.KW; col = i0 - row * p.KW; }
-        row += p.row0;
-        bool stamped[RESOLVE_SLOTS], contested[RESOLVE_SLOTS];
-        uint32_t srow[RESOLVE_SLOTS];
-        bool any_contested = false;
-#pragma unroll
-        for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m) {
-            while (col >= p.KW) { col -= p.KW; ++row; }
-            srow[m] = row;
-            stamped[m] = i0 + 32u * m < n_slots && col == 0u && q.rowmax[row] != 0u;
-            contested[m] = stamped[m] && key[m] != KEY_EMPTY;
-            any_contested |= contested[m];
-            col += 32u;
-        }
-        if (__any_sync(0xFFFFFFFFu, any_contested)) {
-#pragma unroll
-            for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m) {
-                const bool nl = stamp_beats_fragment(p, sc, q, contested[m], srow[m], key_tri(key[m]));
-                if (contested[m] && !nl) stamped[m] = false;   // the wrapped fragment was written after the last stamp
+    if (blockIdx.x == 0u && warp == 0u) {   // the warp that holds the slot at column 0 (lane 0, m = 0)
+        if (p.image && p.KW) {
+            const uint32_t row = row_local + p.row0;
+            const bool stamped = lane == 0u && q.rowmax[row] != 0u;
+            const bool contested = stamped && key[0] != KEY_EMPTY;
+            bool newline = stamped;
+            if (__any_sync(0xFFFFFFFFu, contested)) {   // a wrapped fragment also landed on the stamped cell: who was later?
+                const bool nl = stamp_beats_fragment(p, sc, q, contested, row, key_tri(key[0]));   // all 32 lanes call
+                if (contested) newline = nl;
             }
+            if (newline) c1[0] = (uint32_t)'\n';
         }
-#pragma unroll
-        for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m)
-            if (stamped[m]) c1[m] = (uint32_t)'\n';
+        // image-mode tail, context.rs:38-39: one cell per row behind the frame
+        if (lane == 0u && row_local < n_tail) cells[2u * n_slots + row_local] = blank;
     }
 #pragma unroll
-    for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m) {
-        const uint32_t i = i0 + 32u * m;
-        if (i < n_slots) reinterpret_cast<uint2*>(cells)[i] = make_uint2(c0[m], c1[m]);
-    }
-    // image-mode tail, context.rs:38-39
-    for (uint32_t j = tid; j < n_tail; j += gridDim.x * blockDim.x) cells[2u * n_slots + j] = blank;
+    for (uint32_t m = 0; m < RESOLVE_SLOTS; ++m)
+        if (col0 + 32u * m < p.KW) reinterpret_cast<uint2*>(cells)[i0 + 32u * m] = make_uint2(c0[m], c1[m]);
 }
 
 SLOTH_DEV bool frag_later(const FrameParams& p, unsigned long long ka, uint32_t ida, unsigned long long kb,
