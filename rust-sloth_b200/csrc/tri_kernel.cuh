@@ -258,8 +258,13 @@ SLOTH_DEV size_t t_rowmax_words(uint32_t H) { return ((H + 31u) & ~31u) + 64u; }
 // stamps are shared-memory atomics (ATOMS) instead of generic ones.
 // CONE: the chunks come from the list of super-chunks k_super_pass left over (whole-frame, bounded scenes), followed by
 // the chunks behind the last full super-chunk.
+#ifdef T_MAXNREG   // register cap given directly (A/B builds): what three resident blocks leave goes to the neighbouring frames' kernels
+#define T_BOUNDS __maxnreg__(T_MAXNREG)   // (cannot be combined with __launch_bounds__)
+#else
+#define T_BOUNDS __launch_bounds__(T_WARPS * 32, T_REG_BLOCKS)
+#endif
 template <bool CHECK_REGULAR, bool BAND, bool ROWMAX_SHARED, bool CONE = false>
-__global__ void __launch_bounds__(T_WARPS * 32, T_REG_BLOCKS)
+__global__ void T_BOUNDS
 k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long* __restrict__ keys, const Queues q)
 {
     extern __shared__ __align__(16) unsigned char t_smem[];
