@@ -937,8 +937,10 @@ int build_index(sloth_ctx* c, size_t n_tri)
                 // + room for k_tri's look-ahead past the end of the list (4 iterations of every resident warp), zeroed:
                 // every entry is a valid chunk index at all times
                 CU_IX(cudaMalloc(&c->live_sc[i], ((size_t)n_chunks_all + LIVE_SLACK) * sizeof(uint32_t)));
-                CU_IX(cudaMemset(c->live_sc[i], 0, ((size_t)n_chunks_all + LIVE_SLACK) * sizeof(uint32_t)));
-                if (!tail.empty()) CU_IX(cudaMemcpy(c->live_sc[i], tail.data(), tail.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+                CU_IX(cudaMemsetAsync(c->live_sc[i], 0, ((size_t)n_chunks_all + LIVE_SLACK) * sizeof(uint32_t), c->stream));
+                // (pageable source: staged before the call returns; ordered on c->stream, which is synchronised below)
+                if (!tail.empty())
+                    CU_IX(cudaMemcpyAsync(c->live_sc[i], tail.data(), tail.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
             }
             for (int i = 0; i < 2; ++i) CU_IX(cudaMalloc(&c->skip_sc[i], (size_t)c->n_super * sizeof(uint32_t)));
             for (int i = 0; i < 2; ++i) CU_IX(cudaMalloc(&c->cone_cnt[i], sizeof(ConeCounts)));

@@ -622,3 +622,27 @@ def test_super_chunk_certificate_under_general_matrices():
         assert skipped_some >= 3, skipped_some
     finally:
         ctx.close()
+
+
+def test_left_edge_triangles_and_list_tails():
+    """Triangles whose scan domain ends within three columns of the left edge (the footprint of k_tri hands them to the
+    general path), and scenes whose triangle count leaves chunks behind the last full super-chunk (the static head of
+    k_tri's flat work list) or has no full super-chunk at all: every frame must equal the oracle's."""
+    rng = np.random.default_rng(5)
+    ctx = rs.Context.blank(True)
+    try:
+        for freq, W, H in [(40, 640, 360), (7, 200, 120), (3, 64, 48), (13, 321, 200)]:
+            xyz, rgb, s0 = meshes.icosphere(freq)          # 20 f^2 triangles: 32 000 / 980 / 180 / 3 380
+            ctx.set_scene(xyz, rgb, s0)
+            ctx.resize(W, H)
+            ctx.stats_enable(count_fragments=True)
+            for k, tx in enumerate([-1.0, -0.99, -0.97, -0.9, 0.0]):
+                rot = oracle.rotation(*(rng.random(3) * 6.3)).reshape(4, 4).astype(np.float64)   # column-major
+                rot[3, 0] = tx                              # the sphere's centre lands on x' = (1 + tx) W / 4: at the edge
+                rot = rot.astype(np.float32).reshape(16)
+                ocells, oz, ocnt = oracle.render(xyz, rgb, s0, W, H, rot, image=True, mode=0)
+                cells, z = ctx.render(rot, want_z=True)
+                assert_same(cells, z, ocells, oz, f"f={freq} tx={tx}")
+                assert ctx.stats()["fragments"] == ocnt["covered"], (freq, tx)
+    finally:
+        ctx.close()
