@@ -120,7 +120,7 @@ struct sloth_ctx {
     cudaEvent_t ev_xform[2] = {nullptr, nullptr};
     cudaEvent_t ev_stamped[2] = {nullptr, nullptr};   // k_super_stamp of the set's last frame has read its vxy
     cudaEvent_t ev_batch_start = nullptr;
-    // super-chunks (index.cuh): per-scene cone + unique-vertex list of every 256 triangles, per-frame list of the ones
+    // super-chunks (index.cuh): per-scene cone + unique-vertex list of every SC_TRIS (128) triangles, per-frame list of the ones
     // k_super_cert could not certify as back-facing
     ix::SuperChunk* sc_super = nullptr;
     uint32_t* sc_super_ids = nullptr;

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256) k_ix_connectivity(uint4* __restrict__ rec
 // Super-chunks: SC_CHUNKS consecutive chunks (4 = 128 triangles by default).  Per super-chunk, once per scene:
 //   * the cone of its triangles' object-space normals n_t = (V1-V3) x (V2-V1) (axis, half-angle), the smallest |n_t|
 //     and the longest edge -- the rotation-independent half of the certificate "every triangle of this super-chunk
-//     is back-facing by a margin" that k_super_pass (tri_kernel.cuh) completes per frame;
+//     is back-facing by a margin" that k_super_cert (tri_kernel.cuh) completes per frame;
 //   * the list of its unique vertex ids (at most SC_IDS), from which the row range the super-chunk stamps is read
 //     off without touching its triangles.
 // A super-chunk is certifiable only when it is full, every triangle has a non-zero normal, the cone is narrower than

@@ -51,7 +51,7 @@ struct FrameParams {
     float bf_k;
     uint32_t pf_chunks;   // k_tri: L2 prefetch distance of the record stream in chunks per warp (SLOTH_PF, 0 = off)
     // indexed path, bounded whole-frame scenes: the per-frame half of the super-chunk back-face certificate
-    // (k_super_pass, tri_kernel.cuh).  cone_c = (row 0 of M) x (row 1 of M): the doubled screen area of a triangle is
+    // (k_super_cert, tri_kernel.cuh).  cone_c = (row 0 of M) x (row 1 of M): the doubled screen area of a triangle is
     // cone_c . ((V1-V3) x (V2-V1)); cone_cnorm = |cone_c|, cone_s = max(|row 0|, |row 1|), cone_ev = bound on the
     // rounding error of any computed x' or y' (the last three rounded up).  cone_on = 0: no super-chunk is skipped.
     uint32_t cone_on;
@@ -71,7 +71,7 @@ struct Scene {
     const uint4* __restrict__ rec;     // (i0, i1, i2, triangle << 1 | connected) per triangle, padded to a multiple of 32 with the sentinel vertex
     const float2* __restrict__ vxy;    // (x', y') per unique vertex
     const float* __restrict__ vz;      // z' per unique vertex
-    const uint32_t* __restrict__ super_ids;   // unique vertex ids of every super-chunk of 256 triangles (index.cuh), SC_IDS each
+    const uint32_t* __restrict__ super_ids;   // unique vertex ids of every super-chunk of SC_TRIS triangles (index.cuh), SC_IDS each
 };
 
 // Transformed triangle + everything hoistable out of the per-candidate loop.

@@ -13,16 +13,19 @@
 //                 read record k+2 from its ring slot, start the three (x', y') gathers of chunk k+2
 //                 compute chunk k from its gathered coordinates
 //                 start the copy of record k+4
-//   A  bounds (aabb, rasterizer.rs:58-66), image-mode row stamps (32-row window per chunk, one REDUX.MIN +
-//      one REDUX.OR + one shared-memory ATOMS.MAX), back-face proof with a per-frame distance bound; chunks
-//      that are entirely back-facing (the far side of a closed mesh) end here
-//   B  2 x 3 lockstep footprint for triangles of at most 2 rows x 2 tight columns (separable edge terms)
-//   C  covered FRAGMENTS (not triangles) are parked in a per-warp shared-memory ring (i0, i1, i2, triangle,
-//      x | y << 16); every 32 of them are emitted with all lanes busy -- gather (x', y', z') of the three
-//      vertices, normal / 1/area / depth / glyph, one 64-bit atomicMin into the key plane
+//   A  bounds (aabb, rasterizer.rs:58-66), image-mode row stamps (chunks that hang together: one REDUX.MIN + one
+//      REDUX.MAX + one shared-memory ATOMS.MAX per lane and row; others: a 32-row window and one REDUX.OR), back-face
+//      proof with a per-frame distance bound; chunks that are entirely back-facing (the far side of a closed mesh)
+//      end here
+//   B  2 x 3 lockstep footprint for triangles of at most 2 rows x 2 tight columns (separable edge terms); coverage
+//      compares the row term with the column term (cov_test), the edge values themselves are not needed
+//   C  covered FRAGMENTS (not triangles) are parked in a per-warp shared-memory ring (the triangle's record, which
+//      names the triangle, + x | y << 16); every 32 of them are emitted with all lanes busy -- gather (x', y', z') of
+//      the three vertices, normal / 1/area / depth / glyph, one 64-bit atomicMin into the key plane
 // Larger triangles: up to 8 x 8 candidates one lane each, beyond that row-band items for k_tail; non-finite or
-// huge triangles go to k_tail's brute-force part.  Bit-exactness: every value is produced by the same
-// round-to-nearest operations in the same order as raster_core.cuh's soup path.
+// huge triangles go to k_tail's brute-force part.  Bit-exactness: every emitted value is produced by the same
+// round-to-nearest operations in the same order as raster_core.cuh's soup path; the footprint's coverage decisions use
+// the sign identity fl(a - b) < 0 <=> a < b (cov_test).
 #pragma once
 #include "kernels.cuh"
 #include "index.cuh"
@@ -146,7 +149,7 @@ SLOTH_DEV void t_emit(const FrameParams& p, const Scene& sc, const TRing& wq, ui
 
 // ---------------------------------------------------------------------------------
 // k_super_cert: once per frame, before k_tri (bounded whole-frame scenes of the indexed path), over the
-// super-chunks of 256 triangles (index.cuh).  It completes the back-face certificate for this frame's matrix;
+// super-chunks of SC_TRIS (128) triangles (index.cuh).  It completes the back-face certificate for this frame's matrix;
 // a certified super-chunk never reaches k_tri -- k_super_stamp, which runs between k_tri and the resolve of the frame,
 // stamps the rows its triangles would have stamped; the others are appended to the list k_tri works through.
 //
@@ -256,8 +259,8 @@ SLOTH_DEV size_t t_rowmax_words(uint32_t H) { return ((H + 31u) & ~31u) + 64u; }
 
 // ROWMAX_SHARED: the per-block copy of rowmax lives in dynamic shared memory (frames up to ~8 K rows), so the row
 // stamps are shared-memory atomics (ATOMS) instead of generic ones.
-// CONE: the chunks come from the list of super-chunks k_super_pass left over (whole-frame, bounded scenes), followed by
-// the chunks behind the last full super-chunk.
+// CONE: the chunks come from the flat list k_super_cert left (whole-frame, bounded scenes): the static entries for
+// the chunks behind the last full super-chunk, then the chunks of every super-chunk it could not certify.
 #ifdef T_MAXNREG   // register cap given directly (A/B builds): what three resident blocks leave goes to the neighbouring frames' kernels
 #define T_BOUNDS __maxnreg__(T_MAXNREG)   // (cannot be combined with __launch_bounds__)
 #else

@@ -586,13 +586,13 @@ def test_span_wire_returns_the_same_cells():
 
 
 def test_super_chunk_certificate_under_general_matrices():
-    """k_super_cert skips whole super-chunks of 256 triangles it can prove back-facing for the frame's matrix.  The
+    """k_super_cert skips whole super-chunks (128 triangles) it can prove back-facing for the frame's matrix.  The
     caller's `transform` is any 4x4 (draw_mesh takes it as is, rasterizer.rs:39-46): rotations, anisotropic scale,
     shear, mirror images (which turn the back faces into front faces), translations that push the model half off the
     frame, a collapsed axis.  Every frame must equal the oracle's, newline stamps included, and the plain rotations
     must actually skip something."""
     rng = np.random.default_rng(17)
-    xyz, rgb, s0 = meshes.icosphere(40)                  # 32 000 triangles = 125 super-chunks, ~1 cell each at 640x360
+    xyz, rgb, s0 = meshes.icosphere(40)                  # 32 000 triangles = 250 super-chunks, ~1 cell each at 640x360
     n_chunks = (len(xyz) + 31) // 32
     ctx = rs.Context.blank(True)
     try:
