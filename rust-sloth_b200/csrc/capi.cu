@@ -385,7 +385,12 @@ bool bounded_frame(const sloth_ctx* c, const FrameParams& p)
 
 // whole-frame, bounded: super-chunks certified back-facing for this frame's matrix are taken off k_tri's list
 static constexpr size_t LIVE_SLACK = 65536;   // >= 4 * (warps of the largest k_tri grid: 148 SMs x 4 blocks x 16 warps)
-bool cone_frame(const sloth_ctx* c, const FrameParams& p) { return c->row1 == 0 && !c->tri_pairs && p.cone_on && bounded_frame(c, p); }
+bool cone_frame(const sloth_ctx* c, const FrameParams& p)
+{
+    // (the last condition: k_tri's look-ahead past the end of its work list stays inside the zeroed room behind it)
+    return c->row1 == 0 && !c->tri_pairs && p.cone_on && bounded_frame(c, p) &&
+           (size_t)c->sm_count * c->tri_blocks_per_sm * T_WARPS * 4u <= LIVE_SLACK;
+}
 
 // Everything of the indexed path that can run ahead of k_tri, into frame-state set `set` on stream `st`: Triangle::mul
 // once per unique vertex (k_xform) and, for cone frames, the super-chunk certificate (two lists and their lengths,
