@@ -95,6 +95,16 @@ SLOTH_DEV void sts128(uint32_t a, const uint4& v)
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 SLOTH_DEV void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// if (on) { *(uint4*)a16 = v; *(uint32_t*)a4 = w; } in shared memory, as two predicated stores
+SLOTH_DEV void park_if(bool on, uint32_t a16, const uint4& v, uint32_t a4, uint32_t w)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.u32 p, %0, 0;\n\t"
+                 "@p st.shared.v4.u32 [%1], {%2,%3,%4,%5};\n\t"
+                 "@p st.shared.u32 [%6], %7;\n\t}"
+                 ::"r"((uint32_t)on), "r"(a16), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(a4), "r"(w)
+                 : "memory");
+}
 SLOTH_DEV float2 lds64f(uint32_t a)
 {
     float2 v;
@@ -585,10 +595,9 @@ k_tri(const __grid_constant__ FrameParams p, const Scene sc, unsigned long long*
                 uint32_t o16;   // byte offset of the ring entry (opaque to the compiler, which otherwise goes back to a slot
                                 // index and shifts it twice)
                 asm("and.b32 %0, %1, %2;" : "=r"(o16) : "r"((q_tail + __popc(who & below)) << 4), "n"(T_RING * 16u - 16u));
-                if (has) {
-                    sts128(ring_a + o16, r);
-                    sts32(ring_a + T_RING * 16u + (o16 >> 2), xy0 + bit + (bit >= 3u ? 65536u - 3u : 0u));
-                }
+                // both stores under one predicate instead of a branch around them (the address arithmetic above is harmless
+                // for lanes that have nothing to park)
+                park_if(has, ring_a + o16, r, ring_a + T_RING * 16u + (o16 >> 2), xy0 + bit + (bit >= 3u ? 65536u - 3u : 0u));
                 q_tail += __popc(who);
                 if (q_tail >= q_lim) {
                     __syncwarp();
