@@ -167,3 +167,19 @@ def test_span_expansion_on_the_host():
         rs.expand_spans(np.array([[0, 5], [4, 6], [4, 7]], np.uint32), 10)   # starts must ascend
     with pytest.raises(rs.SlothError):
         rs.expand_spans(np.array([[0, 5], [10, 6]], np.uint32), 10)   # inside the frame
+
+
+def test_bench_traffic_figures_are_committed_and_labelled():
+    """bench.py reports `roofline.traffic` from profiles/traffic.json (DRAM bytes cannot be measured outside ncu): the
+    figures of both kernels it reports must be there, labelled with the capture they came from, and that capture's
+    summary must be a tracked file."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    t = json.load(open(os.path.join(root, "profiles", "traffic.json")))
+    for key in ("k_tri_dram_bytes_per_launch", "k_resolve_even_dram_bytes_per_launch", "k_geom3_dram_bytes_per_launch"):
+        assert isinstance(t[key], int) and t[key] > 0, key
+    assert "ncu --set full" in t["capture"] and t["commit"]
+    summary = t["capture"].split("(")[1].rstrip(")")
+    assert os.path.exists(os.path.join(root, summary)), summary
+    # algorithmic bytes of the bench workload: the dominant kernel must not move more than it is credited with
+    assert t["k_tri_dram_bytes_per_launch"] < 40 * 10_025_280
