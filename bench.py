@@ -20,7 +20,8 @@ frame: update + clear + draw_mesh over the whole scene (main.rs:78-83).
             of the scene): algorithmic 40 B/triangle / its average duration (CUDA events recorded inside
             the library around that kernel, one frame per sample, same frames as the timed region)
             against the measured HBM peak; `frame_frac` is the whole frame (40 N + 4 W H bytes over the
-            batch time per frame) against the same peak.
+            batch time per frame) against the same peak.  `roofline_resolve`: the write-out kernel on 4 bytes per
+            cell, with the fraction its measured DRAM traffic reaches beside it.
 * post_check  after the timed batch the last frame it left on the device is compared with a single
             sloth_render_device of the same rotation (and hashed): the timed path is verified at size.
 * cpu_baseline / --impl reference: the CPU oracle (oracle/sloth_oracle.c, a port: the Rust reference
